@@ -1,0 +1,152 @@
+/*
+ * plip_b200 — C ABI of the B200-native PLIP (CLIP ViT-B/32) inference engine.
+ *
+ * One shared library (libplip_b200.so, nvcc -gencode arch=compute_100a,code=sm_100a) exports
+ * exactly the entry points below.  Plain pointers and sizes only: no torch / python types.
+ *
+ * The reference (PathologyFoundation/plip) has no FFI of its own — its hot path is the Python
+ * call surface of a HuggingFace CLIPModel.  Each entry point therefore cites the reference /
+ * transformers call it replaces ("TF:" = transformers/models/clip/modeling_clip.py, v5.5.0).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; plip_last_error() then holds a
+ *     message (thread-local).  Nothing throws across the ABI.
+ *   - *_dev pointers are device pointers owned by the caller; the engine owns packed weights and
+ *     its workspace (allocated at plip_create, nothing is allocated on the hot path).
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, the device-pointer
+ *     entry points never synchronise.  One handle per device; a handle is not re-entrant.
+ */
+#ifndef PLIP_B200_H_
+#define PLIP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLIP_API __attribute__((visibility("default")))
+
+#define PLIP_B200_ABI_VERSION 1
+
+/* Model constants (TF:configuration_clip.py:47-64,97-109,160-161). */
+#define PLIP_IMAGE_SIZE 224
+#define PLIP_EMBED_DIM 512
+#define PLIP_TEXT_SEQ 77
+#define PLIP_VOCAB 49408
+
+typedef struct plip_engine plip_engine_t;
+
+/* ---- pixel formats accepted by plip_encode_images ------------------------------------------ */
+enum plip_pixel_format {
+  PLIP_PIX_F32_NCHW = 0, /* CLIPProcessor output: normalised float32 [n,3,224,224] (plip.py:35,49) */
+  PLIP_PIX_BF16_NCHW = 1, /* same, bfloat16 */
+  PLIP_PIX_U8_NHWC = 2   /* raw RGB tiles uint8 [n,224,224,3]; (x/255-mean)/std fused on device
+                            (TF:image_processing_clip.py:50-62, embedders/transform.py:51) */
+};
+
+enum plip_id_dtype { PLIP_IDS_I32 = 0, PLIP_IDS_I64 = 1 };
+
+/* ---- errors / version ---------------------------------------------------------------------- */
+PLIP_API const char* plip_last_error(void);
+PLIP_API int plip_abi_version(void);
+/* Kernel launches issued by the library so far (bench.py's gpu_launches accounting). */
+PLIP_API uint64_t plip_launch_count(void);
+
+/* ---- packed weights ------------------------------------------------------------------------ */
+/* The engine consumes ONE contiguous host blob.  Its layout is defined by the library and
+ * queried by the host-side packer (plip_b200/weights.py), which fills it from a HuggingFace
+ * CLIPModel state dict (names listed in SURVEY.md §8a) or an OpenAI-clip state dict.
+ * Replaces CLIPModel.from_pretrained / load_state_dict (plip.py:26, embedders/factory.py:21-25). */
+typedef struct plip_tensor_info {
+  char name[96];    /* HuggingFace-style name, e.g. "vision_model.encoder.layers.0.mlp.fc1.weight" */
+  uint64_t offset;  /* byte offset inside the blob (256-byte aligned) */
+  uint64_t numel;
+  int32_t dtype;    /* 0 = float32, 1 = bfloat16 */
+  int32_t rows;     /* logical 2-D shape (rows x cols), cols == 1 for vectors */
+  int32_t cols;
+  int32_t fused;    /* 0 = plain copy of the named tensor; 1 = q/k/v rows concatenated:
+                       name holds the q tensor, k and v follow ("...q_proj" -> k_proj, v_proj);
+                       the q rows (weight and bias) are pre-scaled by head_dim^-0.5 = 0.125 */
+} plip_tensor_info_t;
+
+PLIP_API int plip_weights_num_tensors(void);
+PLIP_API int plip_weights_tensor_info(int index, plip_tensor_info_t* info);
+PLIP_API uint64_t plip_weights_blob_bytes(void);
+
+/* ---- engine lifetime ----------------------------------------------------------------------- */
+/* host_blob: packed weights (layout above), plus exp(logit_scale) passed separately.
+ * max_micro_batch: largest number of images / captions processed per internal pass; larger calls
+ * are looped in micro-batches.  Device memory: blob + plip_workspace_bytes(max_micro_batch). */
+PLIP_API int plip_create(const void* host_blob, uint64_t blob_bytes, float logit_scale_exp, int device,
+                         int max_micro_batch, plip_engine_t** out);
+PLIP_API int plip_destroy(plip_engine_t* e);
+PLIP_API uint64_t plip_workspace_bytes(int max_micro_batch);
+PLIP_API float plip_logit_scale_exp(const plip_engine_t* e);
+PLIP_API int plip_max_micro_batch(const plip_engine_t* e);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+/* Vision tower + visual_projection: replaces CLIPModel.get_image_features (TF:829-863, called at
+ * plip.py:50) and OpenAI-clip model.encode_image (embedders/plip.py:48).
+ * out_dev: float32 [n,512]; normalize != 0 divides each row by its L2 norm (TF:57-65,923). */
+PLIP_API int plip_encode_images(plip_engine_t* e, const void* pixels_dev, int pixel_format, int64_t n,
+                                float* out_dev, int normalize, void* stream);
+
+/* Text tower + text_projection: replaces CLIPModel.get_text_features (TF:793-825, called at
+ * plip.py:68) and model.encode_text (embedders/plip.py:66).
+ * ids_dev: [n,seq_len] token ids (seq_len <= 77); attention_mask_dev: optional [n,seq_len] of the
+ * same dtype (0 = padded key), NULL = no padding mask.  Pooling takes the row of the first
+ * eos_token_id (49407), as TF:571-584. */
+PLIP_API int plip_encode_text(plip_engine_t* e, const void* ids_dev, int ids_dtype,
+                              const void* attention_mask_dev, int64_t n, int seq_len, float* out_dev,
+                              int normalize, void* stream);
+
+/* Similarity head: logits_per_image[n,m] = scale * norm(img)[n,512] . norm(txt)[m,512]^T
+ * (TF:923-930; numpy versions at plip.py:73-76, evaluation/zero_shot/zero_shot.py:12,
+ * evaluation/retrieval/retrieval.py:14).  normalize_img / normalize_txt select which side is
+ * L2-normalised on the fly (PLIP._cosine_similarity normalises only the key side). */
+PLIP_API int plip_similarity(const float* img_dev, int64_t n, const float* txt_dev, int64_t m, float scale,
+                             int normalize_img, int normalize_txt, float* logits_dev, int64_t ld_logits,
+                             void* stream);
+
+/* Fused similarity + top-k over the second operand (k <= 64), never materialising [n,m]:
+ * idx_dev int32 [n,k] (descending score), val_dev float32 [n,k] (may be NULL).
+ * Replaces np.argmax (plip.py:102, zero_shot.py:13) and argsort()[:, -k:][:, ::-1]
+ * (plip.py:85, retrieval.py:16). */
+PLIP_API int plip_similarity_topk(const float* query_dev, int64_t n, const float* space_dev, int64_t m,
+                                  float scale, int normalize_query, int normalize_space, int k,
+                                  int32_t* idx_dev, float* val_dev, void* stream);
+
+/* L2-normalise rows in place (embedders/plip.py:53,73). */
+PLIP_API int plip_l2_normalize(float* x_dev, int64_t n, int dim, void* stream);
+
+/* ---- host-buffer convenience (end-to-end path; copies are inside the call) ------------------- */
+/* pixels_host / ids_host / out_host are host pointers (pinned or pageable).  The call stages
+ * micro-batches through pinned buffers on two streams (H2D overlapped with compute), writes the
+ * float32 [n,512] result to out_host and returns after the last D2H completed. */
+PLIP_API int plip_encode_images_host(plip_engine_t* e, const void* pixels_host, int pixel_format, int64_t n,
+                                     float* out_host, int normalize);
+PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int ids_dtype,
+                                   const void* attention_mask_host, int64_t n, int seq_len,
+                                   float* out_host, int normalize);
+
+/* ---- per-kernel test hooks (used by tests/ only; stream-ordered, device pointers) ------------ */
+PLIP_API int plip_dbg_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K,
+                           const float* bias, void* out, int ldo, const float* pos, int epilogue, int cta_group,
+                           int block_n, void* stream);
+PLIP_API int plip_dbg_layernorm(const float* x, int64_t rows, int dim, int64_t in_row_stride,
+                                const float* gamma, const float* beta, float* out_f32, void* out_bf16,
+                                void* stream);
+PLIP_API int plip_dbg_attention(const void* qkv_bf16, int64_t n_seq, int seq_len, int heads, int causal,
+                                const int32_t* key_mask, void* out_bf16, void* stream);
+PLIP_API int plip_dbg_im2col(const void* pixels, int pixel_format, int64_t n, void* out_bf16, void* stream);
+/* Run one tower and copy the fp32 residual stream [n*S, D] after `num_layers` encoder layers
+ * (0 = after embeddings / pre-LN) into hidden_dev.  tower: 0 = vision (input pixels), 1 = text. */
+PLIP_API int plip_dbg_hidden_states(plip_engine_t* e, int tower, const void* input_dev, int input_format,
+                                    const void* attention_mask_dev, int64_t n, int num_layers,
+                                    float* hidden_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLIP_B200_H_ */
