@@ -1,0 +1,288 @@
+// plip_b200 — fused attention core on tcgen05: S = Q K^T -> masked softmax -> O = P V, one kernel.
+//
+// Replaces F.scaled_dot_product_attention / eager_attention_forward for the CLIP towers
+// (TF:integrations/sdpa_attention.py:92-101, TF:modeling_clip.py:261-279): per (sequence, head)
+//     softmax(q k^T * dh^-0.5 + mask, fp32) v,   dh = 64,
+// vision S = 50 without mask, text S <= 77 with the causal (+ key padding) mask (TF:546-557).
+// The dh^-0.5 = 0.125 scale is folded into the q rows of the packed QKV weights (exact: power of 2).
+//
+// Sequences are short, so G = floor(128 / S) consecutive sequences of one head are packed into one
+// 128-row UMMA tile (vision: 2 images = 100 rows; text: 1 caption = 77 rows) and attention between
+// different sequences is masked out (block-diagonal), which keeps the arithmetic exact:
+//   TMA      Q,K,V head slices [128 rows x 64] of the QKV activation -> smem (128B swizzle), 2-stage ring
+//   MMA 1    S[128x128] (TMEM, fp32) = Q (smem, K-major) x K^T (smem, K-major)         4 x UMMA 128x128x16
+//   softmax  thread == query row: tcgen05.ld S, mask, max, exp2, row sum; P (bf16) -> TMEM via tcgen05.st
+//   MMA 2    O[128x64] (TMEM, fp32) = P (TMEM, A operand) x V (smem, MN-major)          8 x UMMA 128x64x16
+//   epilogue tcgen05.ld O, multiply by 1/rowsum, bf16 -> global (head slice of the [rows, D] output)
+// 5 warps: warps 0-3 = softmax/epilogue (one TMEM lane quarter each), warp 4 = TMA + MMA issuer.
+// TMEM: S 128 cols + P 64 cols + O 64 cols = 256 -> two CTAs co-reside per SM and overlap each other.
+#include "kernels.cuh"
+
+namespace plip {
+
+namespace {
+
+constexpr int kAttThreads = 160;
+constexpr uint32_t kTileBytes = 128 * 64 * 2;  // one [128 x 64] bf16 operand tile
+constexpr uint32_t kStageBytes = 3 * kTileBytes;
+constexpr uint32_t kAttSmem = 2 * kStageBytes + 1024 + 256;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+      "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+      "r"(v[15])
+      : "memory");
+}
+
+struct AttParams {
+  int64_t total_rows;   // n_seq * seq_len
+  int seq_len;          // S
+  int group;            // G sequences per tile
+  int rows_per_tile;    // R = G * S
+  int heads;
+  int64_t seq_tiles;    // ceil(n_seq / G)
+  int causal;
+  const int32_t* key_mask;  // [n_seq, S] or nullptr
+  __nv_bfloat16* out;       // [total_rows, heads*64]
+};
+
+__global__ void __launch_bounds__(kAttThreads, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_raw_u32 = smem_u32(smem_raw);
+  const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + 2 * kStageBytes;
+  auto bar_load = [&](int s) { return bar_base + 8u * s; };
+  const uint32_t bar_s = bar_base + 16, bar_p = bar_base + 24, bar_o = bar_base + 32;
+  const uint32_t tmem_slot = bar_base + 40;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int D = p.heads * kHeadDim;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(bar_load(0), 1);
+    mbar_init(bar_load(1), 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<1>(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base =
+      *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
+
+  const int64_t num_tiles = p.seq_tiles * p.heads;
+
+  if (warp == 4) {
+    // ===================== TMA producer + MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S = Q K^T, both K-major
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // O = P V, V is MN-major
+      auto issue_load = [&](int64_t tile, int stage) {
+        const int64_t st = tile / p.heads;
+        const int h = (int)(tile - st * p.heads);
+        const int32_t row0 = (int32_t)(st * p.rows_per_tile);
+        const uint32_t dst = smem_base + stage * kStageBytes;
+        mbar_arrive_expect_tx(bar_load(stage), kStageBytes);
+        tma_load_2d(dst, &tmQKV, bar_load(stage), h * kHeadDim, row0);
+        tma_load_2d(dst + kTileBytes, &tmQKV, bar_load(stage), D + h * kHeadDim, row0);
+        tma_load_2d(dst + 2 * kTileBytes, &tmQKV, bar_load(stage), 2 * D + h * kHeadDim, row0);
+      };
+      int64_t tile = blockIdx.x;
+      if (tile < num_tiles) issue_load(tile, 0);
+      uint32_t it = 0;
+      for (; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const int64_t next = tile + gridDim.x;
+        if (next < num_tiles) issue_load(next, stage ^ 1);  // previous user of that stage finished (bar_o)
+        mbar_wait(bar_load(stage), (it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t sq = smem_base + stage * kStageBytes;
+        const uint64_t qdesc = make_smem_desc_sw128(sq, 1024, 16);
+        const uint64_t kdesc = make_smem_desc_sw128(sq + kTileBytes, 1024, 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss<1>(tmem_base + kColS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit<1>(bar_s);
+        // wait for the softmax warps to publish P in TMEM
+        mbar_wait(bar_p, it & 1u);
+        tc_fence_after();
+        const uint32_t sv = sq + 2 * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // V tile [128 keys][64 dh]: advancing 16 keys (one UMMA K) = 16 rows of 128 B
+          const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, 1024, 1024);
+          umma_ts(tmem_base + kColO, tmem_base + kColP + k * 8, vdesc, idesc_o, k != 0 ? 1u : 0u);
+        }
+        umma_commit<1>(bar_o);
+        mbar_wait(bar_o, it & 1u);  // smem stage and S/P columns are free again
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue (thread == query row) =====================
+    const int r = threadIdx.x;  // 0..127 == TMEM lane
+    const int S = p.seq_len;
+    const int seq_r = r / S;
+    const int pos_r = r - seq_r * S;
+    const bool row_in_tile = r < p.rows_per_tile;
+    const int c_lo = seq_r * S;
+    const int c_hi = row_in_tile ? (c_lo + (p.causal ? pos_r + 1 : S)) : c_lo;  // empty range for pad rows
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int64_t st = tile / p.heads;
+      const int h = (int)(tile - st * p.heads);
+      const int64_t row0 = st * p.rows_per_tile;
+
+      // per-chunk validity masks (bit c = key column 32*j + c may be attended by this row)
+      uint32_t valid[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int lo = max(c_lo - 32 * j, 0), hi = min(c_hi - 32 * j, 32);
+        uint32_t m = 0;
+        if (hi > lo) m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+        if (p.key_mask != nullptr) {
+          const int c = 32 * j + lane;
+          const int64_t grow = row0 + c;
+          const bool kv = (c < p.rows_per_tile) && (grow < p.total_rows) && (p.key_mask[grow] != 0);
+          m &= __ballot_sync(0xffffffffu, kv);
+        }
+        valid[j] = m;
+      }
+
+      mbar_wait(bar_s, it & 1u);
+      tc_fence_after();
+
+      // pass 1: row maximum over the valid columns
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        if (__any_sync(0xffffffffu, valid[j] != 0)) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + kColS + 32 * j, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if ((valid[j] >> c) & 1u) mx = fmaxf(mx, __uint_as_float(v[c]));
+        }
+      }
+      const float mx_s = (mx == -INFINITY) ? 0.f : mx * kLog2e;
+
+      // pass 2: p = exp(s - max), row sum, P (bf16) -> TMEM
+      float sum = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t pk[16];
+        if (__any_sync(0xffffffffu, valid[j] != 0)) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + kColS + 32 * j, v);
+          tmem_ld_wait();
+          float e[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float x = exp2f(fmaf(__uint_as_float(v[c]), kLog2e, -mx_s));
+            e[c] = ((valid[j] >> c) & 1u) ? x : 0.f;
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            // the row sum uses the bf16-rounded probabilities the PV product will actually see
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(e[2 * c], e[2 * c + 1]);
+            sum += __low2float(h2) + __high2float(h2);
+            pk[c] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) pk[c] = 0u;
+        }
+        tmem_st16(lane_base + kColP + 16 * j, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+
+      // epilogue: O / rowsum -> bf16 head slice
+      mbar_wait(bar_o, it & 1u);
+      tc_fence_after();
+      const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+      const int64_t grow = row0 + r;
+      const bool store = row_in_tile && grow < p.total_rows;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t v[32];
+        tmem_ld32(lane_base + kColO + 32 * j, v);
+        tmem_ld_wait();
+        if (store) {
+          uint4* o4 = reinterpret_cast<uint4*>(p.out + grow * D + h * kHeadDim + 32 * j);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
+            o4[q] = u;
+          }
+        }
+      }
+      tc_fence_before();  // order our TMEM reads before the next tile's MMAs (via bar_p of that tile)
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<1>(tmem_base, kTmemCols);
+}
+
+}  // namespace
+
+int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int heads, bool causal,
+                     const int32_t* key_mask, __nv_bfloat16* out, cudaStream_t st) {
+  PLIP_REQUIRE(n_seq > 0 && seq_len > 0 && seq_len <= 128, "attention: bad shape n_seq=%lld seq_len=%d",
+               (long long)n_seq, seq_len);
+  PLIP_REQUIRE(heads > 0 && heads <= 16, "attention: bad head count %d", heads);
+  static bool configured = false;
+  static int grid_cap = 0;
+  if (!configured) {
+    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kAttSmem));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    grid_cap = 2 * sms;
+    configured = true;
+  }
+  const int D = heads * kHeadDim;
+  const int64_t rows = n_seq * seq_len;
+  CUtensorMap tm;
+  if (int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D * 2, 128, 64)) return rc;
+  AttParams p;
+  p.total_rows = rows;
+  p.seq_len = seq_len;
+  p.group = 128 / seq_len;
+  p.rows_per_tile = p.group * seq_len;
+  p.heads = heads;
+  p.seq_tiles = (n_seq + p.group - 1) / p.group;
+  p.causal = causal ? 1 : 0;
+  p.key_mask = key_mask;
+  p.out = out;
+  const int64_t tiles = p.seq_tiles * heads;
+  const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
+  attention_kernel<<<grid, kAttThreads, kAttSmem, st>>>(tm, p);
+  PLIP_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+}  // namespace plip

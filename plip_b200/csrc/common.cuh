@@ -126,9 +126,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
                : "memory");
 }
 // Arrive on a barrier that may live in another CTA of the cluster (shared::cluster address).
+// Plain (CTA-scope release) form: a .release.cluster arrive compiles to MEMBAR.ALL.GPU, which
+// drains every outstanding global store of the thread and serialised the 2-CTA pipeline (ncu r1).
+// The signals sent this way only order tcgen05 / TMA work, which has its own fences.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;

@@ -1,0 +1,598 @@
+// plip_b200 — engine: packed weights, workspace, tower orchestration, C ABI (include/plip_b200.h).
+//
+// The forward pass of one micro-batch is a fixed sequence of stream-ordered kernel launches:
+//   vision (TF:modeling_clip.py:667-691, 829-863)
+//     im2col(+u8 normalise) -> patch GEMM (+pos emb, scatter past the class row) -> class rows -> pre-LN
+//     12 x [ LN1 -> QKV GEMM(+bias) -> fused attention -> out GEMM(+bias +residual)
+//            LN2 -> fc1 GEMM(+bias +QuickGELU) -> fc2 GEMM(+bias +residual) ]
+//     CLS-row post-LN -> projection GEMM [-> L2 normalise]
+//   text (TF:531-589, 793-825): token+pos gather & EOS search -> same 12 layers (causal/padding mask)
+//     -> EOS-row final-LN -> projection GEMM [-> L2 normalise]
+// Residual stream fp32 (X), GEMM operands bf16 (Xn, QKV, H): cosine >= 1-1e-4 vs the fp32 reference
+// needs the fp32 residual/LN/softmax.  No allocation and no host sync on this path.
+#include "kernels.cuh"
+
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+namespace plip {
+const char* get_last_error();
+
+namespace {
+
+struct Spec {
+  std::string name;
+  int dtype;  // 0 f32, 1 bf16
+  int rows, cols, fused;
+  uint64_t offset, numel;
+};
+
+void add(std::vector<Spec>& v, const std::string& name, int dtype, int rows, int cols, int fused = 0) {
+  Spec s;
+  s.name = name; s.dtype = dtype; s.rows = rows; s.cols = cols; s.fused = fused;
+  s.numel = (uint64_t)rows * cols;
+  s.offset = 0;
+  v.push_back(s);
+}
+
+void add_tower(std::vector<Spec>& v, const std::string& pfx, int D, int FF) {
+  for (int l = 0; l < kLayers; ++l) {
+    const std::string p = pfx + ".encoder.layers." + std::to_string(l);
+    add(v, p + ".layer_norm1.weight", 0, D, 1);
+    add(v, p + ".layer_norm1.bias", 0, D, 1);
+    add(v, p + ".self_attn.q_proj.weight", 1, 3 * D, D, 1);  // q|k|v rows, q pre-scaled by 0.125
+    add(v, p + ".self_attn.q_proj.bias", 0, 3 * D, 1, 1);
+    add(v, p + ".self_attn.out_proj.weight", 1, D, D);
+    add(v, p + ".self_attn.out_proj.bias", 0, D, 1);
+    add(v, p + ".layer_norm2.weight", 0, D, 1);
+    add(v, p + ".layer_norm2.bias", 0, D, 1);
+    add(v, p + ".mlp.fc1.weight", 1, FF, D);
+    add(v, p + ".mlp.fc1.bias", 0, FF, 1);
+    add(v, p + ".mlp.fc2.weight", 1, D, FF);
+    add(v, p + ".mlp.fc2.bias", 0, D, 1);
+  }
+}
+
+const std::vector<Spec>& specs() {
+  static std::vector<Spec> v;
+  if (!v.empty()) return v;
+  add(v, "vision_model.embeddings.patch_embedding.weight", 1, kVisDim, kPatchK);
+  add(v, "vision_model.embeddings.class_embedding", 0, kVisDim, 1);
+  add(v, "vision_model.embeddings.position_embedding.weight", 0, kVisSeq, kVisDim);
+  add(v, "vision_model.pre_layrnorm.weight", 0, kVisDim, 1);
+  add(v, "vision_model.pre_layrnorm.bias", 0, kVisDim, 1);
+  add_tower(v, "vision_model", kVisDim, kVisFF);
+  add(v, "vision_model.post_layernorm.weight", 0, kVisDim, 1);
+  add(v, "vision_model.post_layernorm.bias", 0, kVisDim, 1);
+  add(v, "visual_projection.weight", 1, kProj, kVisDim);
+  add(v, "text_model.embeddings.token_embedding.weight", 0, kVocab, kTxtDim);
+  add(v, "text_model.embeddings.position_embedding.weight", 0, kTxtSeq, kTxtDim);
+  add_tower(v, "text_model", kTxtDim, kTxtFF);
+  add(v, "text_model.final_layer_norm.weight", 0, kTxtDim, 1);
+  add(v, "text_model.final_layer_norm.bias", 0, kTxtDim, 1);
+  add(v, "text_projection.weight", 1, kProj, kTxtDim);
+  uint64_t off = 0;
+  for (auto& s : v) {
+    s.offset = off;
+    off += s.numel * (s.dtype == 1 ? 2 : 4);
+    off = (off + 255) & ~255ull;
+  }
+  return v;
+}
+
+uint64_t blob_bytes() {
+  const auto& v = specs();
+  const Spec& s = v.back();
+  return (s.offset + s.numel * (s.dtype == 1 ? 2 : 4) + 255) & ~255ull;
+}
+
+struct LayerW {
+  const float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *b1, *b2;
+  const __nv_bfloat16 *wqkv, *wo, *w1, *w2;
+};
+
+constexpr int kEosId = 49407;  // TF:configuration_clip.py:63 (eos_token_id)
+
+size_t pixel_bytes(int fmt) {
+  const size_t px = (size_t)3 * kImage * kImage;
+  return fmt == PLIP_PIX_F32_NCHW ? px * 4 : (fmt == PLIP_PIX_BF16_NCHW ? px * 2 : px);
+}
+
+}  // namespace
+}  // namespace plip
+
+using namespace plip;
+
+struct plip_engine {
+  int device = 0;
+  int max_mb = 0;
+  float logit_scale_exp = 1.f;
+  uint8_t* d_blob = nullptr;
+  // vision
+  const __nv_bfloat16 *v_patch_w = nullptr, *v_proj = nullptr;
+  const float *v_cls = nullptr, *v_pos = nullptr, *v_pre_g = nullptr, *v_pre_b = nullptr, *v_post_g = nullptr,
+              *v_post_b = nullptr;
+  LayerW vis[kLayers], txt[kLayers];
+  // text
+  const float *t_tok = nullptr, *t_pos = nullptr, *t_fin_g = nullptr, *t_fin_b = nullptr;
+  const __nv_bfloat16* t_proj = nullptr;
+  // workspace (sized for max_mb)
+  float* X = nullptr;            // residual stream fp32 [rows, D]
+  __nv_bfloat16* Xn = nullptr;   // LN output / attention output [rows, D]
+  __nv_bfloat16* QKV = nullptr;  // [rows, 3D]
+  __nv_bfloat16* H = nullptr;    // fc1 output [rows, FF]; aliases the im2col matrix [mb*49, 3072]
+  __nv_bfloat16* pooled = nullptr;  // [mb, 768]
+  int32_t* row_idx = nullptr;       // [mb] EOS rows
+  int32_t* kmask = nullptr;         // [mb*77] key padding mask
+  // host-buffer path (lazy)
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  void* d_in[2] = {nullptr, nullptr};
+  size_t d_in_bytes = 0;
+  void* h_stage[2] = {nullptr, nullptr};
+  size_t h_stage_bytes = 0;
+  float* d_out = nullptr;
+  size_t d_out_bytes = 0;
+  void* d_aux = nullptr;  // ids + mask for the text host path
+  size_t d_aux_bytes = 0;
+};
+
+namespace {
+
+template <typename T>
+const T* wptr(const plip_engine* e, const Spec& s) {
+  return reinterpret_cast<const T*>(e->d_blob + s.offset);
+}
+
+int bind_weights(plip_engine* e) {
+  const auto& v = specs();
+  size_t i = 0;
+  auto nextf = [&]() { return wptr<float>(e, v[i++]); };
+  auto nextb = [&]() { return wptr<__nv_bfloat16>(e, v[i++]); };
+  auto tower = [&](LayerW* L) {
+    for (int l = 0; l < kLayers; ++l) {
+      L[l].ln1_g = nextf(); L[l].ln1_b = nextf();
+      L[l].wqkv = nextb(); L[l].bqkv = nextf();
+      L[l].wo = nextb(); L[l].bo = nextf();
+      L[l].ln2_g = nextf(); L[l].ln2_b = nextf();
+      L[l].w1 = nextb(); L[l].b1 = nextf();
+      L[l].w2 = nextb(); L[l].b2 = nextf();
+    }
+  };
+  e->v_patch_w = nextb();
+  e->v_cls = nextf();
+  e->v_pos = nextf();
+  e->v_pre_g = nextf(); e->v_pre_b = nextf();
+  tower(e->vis);
+  e->v_post_g = nextf(); e->v_post_b = nextf();
+  e->v_proj = nextb();
+  e->t_tok = nextf();
+  e->t_pos = nextf();
+  tower(e->txt);
+  e->t_fin_g = nextf(); e->t_fin_b = nextf();
+  e->t_proj = nextb();
+  PLIP_REQUIRE(i == v.size(), "internal: weight table mismatch (%zu vs %zu)", i, v.size());
+  return 0;
+}
+
+struct WsLayout {
+  size_t x, xn, qkv, h, pooled, rowidx, kmask, total;
+};
+
+WsLayout ws_layout(int mb) {
+  const size_t rv = (size_t)mb * kVisSeq, rt = (size_t)mb * kTxtSeq;
+  auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+  auto al = [](size_t a) { return (a + 1023) & ~(size_t)1023; };
+  WsLayout w;
+  size_t off = 0;
+  w.x = off; off += al(mx(rv * kVisDim, rt * kTxtDim) * 4);
+  w.xn = off; off += al(mx(rv * kVisDim, rt * kTxtDim) * 2);
+  w.qkv = off; off += al(mx(rv * 3 * kVisDim, rt * 3 * kTxtDim) * 2);
+  w.h = off; off += al(mx(mx(rv * kVisFF, rt * kTxtFF), (size_t)mb * kPatches * kPatchK) * 2);
+  w.pooled = off; off += al((size_t)mb * kVisDim * 2);
+  w.rowidx = off; off += al((size_t)mb * 4);
+  w.kmask = off; off += al(rt * 4);
+  w.total = off;
+  return w;
+}
+
+int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int FF, int heads, bool causal,
+               const int32_t* kmask, int num_layers, cudaStream_t st) {
+  const int64_t M = n_seq * S;
+  PLIP_REQUIRE(M <= 0x7fffffff / 4, "micro-batch too large");
+  for (int l = 0; l < num_layers; ++l) {
+    const LayerW& w = L[l];
+    // x = x + out_proj(attn(LN1(x)))                                     TF:modeling_clip.py:370-377
+    if (int rc = launch_layernorm(e->X, nullptr, D, M, D, w.ln1_g, w.ln1_b, nullptr, e->Xn, st)) return rc;
+    GemmArgs g;
+    g.A = e->Xn; g.lda = D; g.W = w.wqkv; g.ldw = D; g.M = (int)M; g.N = 3 * D; g.K = D;
+    g.bias = w.bqkv; g.out = e->QKV; g.ldo = 3 * D; g.epi = EPI_BIAS_BF16;
+    if (int rc = launch_gemm(g, st)) return rc;
+    if (int rc = launch_attention(e->QKV, n_seq, S, heads, causal, kmask, e->Xn, st)) return rc;
+    g = GemmArgs();
+    g.A = e->Xn; g.lda = D; g.W = w.wo; g.ldw = D; g.M = (int)M; g.N = D; g.K = D;
+    g.bias = w.bo; g.out = e->X; g.ldo = D; g.epi = EPI_BIAS_RESID_F32;
+    if (int rc = launch_gemm(g, st)) return rc;
+    // x = x + fc2(quick_gelu(fc1(LN2(x))))                                TF:modeling_clip.py:379-382
+    if (int rc = launch_layernorm(e->X, nullptr, D, M, D, w.ln2_g, w.ln2_b, nullptr, e->Xn, st)) return rc;
+    g = GemmArgs();
+    g.A = e->Xn; g.lda = D; g.W = w.w1; g.ldw = D; g.M = (int)M; g.N = FF; g.K = D;
+    g.bias = w.b1; g.out = e->H; g.ldo = FF; g.epi = EPI_BIAS_GELU_BF16;
+    if (int rc = launch_gemm(g, st)) return rc;
+    g = GemmArgs();
+    g.A = e->H; g.lda = FF; g.W = w.w2; g.ldw = FF; g.M = (int)M; g.N = D; g.K = FF;
+    g.bias = w.b2; g.out = e->X; g.ldo = D; g.epi = EPI_BIAS_RESID_F32;
+    if (int rc = launch_gemm(g, st)) return rc;
+  }
+  return 0;
+}
+
+// Vision tower up to (and including) `num_layers` encoder layers; X holds the residual stream.
+int vision_trunk(plip_engine* e, const void* pixels, int fmt, int64_t mb, int num_layers, cudaStream_t st) {
+  if (int rc = launch_im2col(pixels, fmt, mb, e->H, st)) return rc;
+  GemmArgs g;
+  g.A = e->H; g.lda = kPatchK; g.W = e->v_patch_w; g.ldw = kPatchK;
+  g.M = (int)(mb * kPatches); g.N = kVisDim; g.K = kPatchK;
+  g.out = e->X; g.ldo = kVisDim; g.pos = e->v_pos; g.epi = EPI_PATCH_F32;
+  if (int rc = launch_gemm(g, st)) return rc;
+  if (int rc = launch_cls_rows(e->v_cls, e->v_pos, mb, e->X, st)) return rc;
+  const int64_t M = mb * kVisSeq;
+  if (int rc = launch_layernorm(e->X, nullptr, kVisDim, M, kVisDim, e->v_pre_g, e->v_pre_b, e->X, nullptr, st)) return rc;
+  return run_layers(e, e->vis, mb, kVisSeq, kVisDim, kVisFF, kVisHeads, false, nullptr, num_layers, st);
+}
+
+int vision_forward(plip_engine* e, const void* pixels, int fmt, int64_t mb, float* out, int normalize,
+                   cudaStream_t st) {
+  if (int rc = vision_trunk(e, pixels, fmt, mb, kLayers, st)) return rc;
+  // pooled = post_layernorm(last_hidden_state[:, 0, :])                  TF:modeling_clip.py:685-686
+  if (int rc = launch_layernorm(e->X, nullptr, (int64_t)kVisSeq * kVisDim, mb, kVisDim, e->v_post_g, e->v_post_b,
+                                nullptr, e->pooled, st)) return rc;
+  GemmArgs g;
+  g.A = e->pooled; g.lda = kVisDim; g.W = e->v_proj; g.ldw = kVisDim;
+  g.M = (int)mb; g.N = kProj; g.K = kVisDim; g.out = out; g.ldo = kProj; g.epi = EPI_F32;
+  if (int rc = launch_gemm(g, st)) return rc;
+  if (normalize) return launch_l2_normalize(out, mb, kProj, st);
+  return 0;
+}
+
+int text_trunk(plip_engine* e, const void* ids, int ids_dtype, const void* mask, int64_t mb, int S,
+               int num_layers, cudaStream_t st) {
+  if (int rc = launch_text_embed(ids, ids_dtype, mb, S, e->t_tok, e->t_pos, e->X, e->row_idx, kEosId, st)) return rc;
+  const int32_t* km = nullptr;
+  if (mask) {
+    if (int rc = launch_mask_to_i32(mask, ids_dtype, mb * S, e->kmask, st)) return rc;
+    km = e->kmask;
+  }
+  return run_layers(e, e->txt, mb, S, kTxtDim, kTxtFF, kTxtHeads, true, km, num_layers, st);
+}
+
+int text_forward(plip_engine* e, const void* ids, int ids_dtype, const void* mask, int64_t mb, int S, float* out,
+                 int normalize, cudaStream_t st) {
+  if (int rc = text_trunk(e, ids, ids_dtype, mask, mb, S, kLayers, st)) return rc;
+  // pooled = final_layer_norm(last_hidden_state)[b, first eos]            TF:modeling_clip.py:562-584
+  if (int rc = launch_layernorm(e->X, e->row_idx, kTxtDim, mb, kTxtDim, e->t_fin_g, e->t_fin_b, nullptr,
+                                e->pooled, st)) return rc;
+  GemmArgs g;
+  g.A = e->pooled; g.lda = kTxtDim; g.W = e->t_proj; g.ldw = kTxtDim;
+  g.M = (int)mb; g.N = kProj; g.K = kTxtDim; g.out = out; g.ldo = kProj; g.epi = EPI_F32;
+  if (int rc = launch_gemm(g, st)) return rc;
+  if (normalize) return launch_l2_normalize(out, mb, kProj, st);
+  return 0;
+}
+
+int ensure_host_path(plip_engine* e) {
+  if (e->s_compute) return 0;
+  PLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+  PLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    PLIP_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
+    PLIP_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+int grow_dev(void** p, size_t* have, size_t want) {
+  if (*have >= want) return 0;
+  if (*p) PLIP_CUDA_CHECK(cudaFree(*p));
+  *p = nullptr; *have = 0;
+  PLIP_CUDA_CHECK(cudaMalloc(p, want));
+  *have = want;
+  return 0;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+PLIP_API const char* plip_last_error(void) { return plip::get_last_error(); }
+PLIP_API int plip_abi_version(void) { return PLIP_B200_ABI_VERSION; }
+PLIP_API uint64_t plip_launch_count(void) { return plip::g_launch_count; }
+
+PLIP_API int plip_weights_num_tensors(void) { return (int)specs().size(); }
+
+PLIP_API int plip_weights_tensor_info(int index, plip_tensor_info_t* info) {
+  const auto& v = specs();
+  PLIP_REQUIRE(info != nullptr && index >= 0 && index < (int)v.size(), "tensor_info: index %d out of range", index);
+  memset(info, 0, sizeof(*info));
+  strncpy(info->name, v[index].name.c_str(), sizeof(info->name) - 1);
+  info->offset = v[index].offset;
+  info->numel = v[index].numel;
+  info->dtype = v[index].dtype;
+  info->rows = v[index].rows;
+  info->cols = v[index].cols;
+  info->fused = v[index].fused;
+  return 0;
+}
+
+PLIP_API uint64_t plip_weights_blob_bytes(void) { return blob_bytes(); }
+
+PLIP_API uint64_t plip_workspace_bytes(int max_micro_batch) {
+  return max_micro_batch > 0 ? ws_layout(max_micro_batch).total : 0;
+}
+
+PLIP_API int plip_create(const void* host_blob, uint64_t nbytes, float logit_scale_exp, int device,
+                         int max_micro_batch, plip_engine_t** out) {
+  PLIP_REQUIRE(out != nullptr && host_blob != nullptr, "plip_create: null argument");
+  PLIP_REQUIRE(nbytes == blob_bytes(), "plip_create: blob is %llu bytes, expected %llu",
+               (unsigned long long)nbytes, (unsigned long long)blob_bytes());
+  PLIP_REQUIRE(max_micro_batch >= 1 && max_micro_batch <= 8192, "plip_create: max_micro_batch %d out of [1,8192]",
+               max_micro_batch);
+  int ndev = 0;
+  PLIP_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  PLIP_REQUIRE(device >= 0 && device < ndev, "plip_create: device %d not present (%d devices)", device, ndev);
+  PLIP_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PLIP_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  PLIP_REQUIRE(prop.major == 10, "plip_create: device %d is sm_%d%d; this library is built for sm_100a only",
+               device, prop.major, prop.minor);
+  plip_engine* e = new plip_engine();
+  e->device = device;
+  e->max_mb = max_micro_batch;
+  e->logit_scale_exp = logit_scale_exp;
+  const WsLayout w = ws_layout(max_micro_batch);
+  uint8_t* ws = nullptr;
+  if (cudaMalloc(&e->d_blob, nbytes) != cudaSuccess || cudaMalloc(&ws, w.total) != cudaSuccess) {
+    set_last_error("plip_create: cudaMalloc of %llu + %llu bytes failed: %s", (unsigned long long)nbytes,
+                   (unsigned long long)w.total, cudaGetErrorString(cudaGetLastError()));
+    if (e->d_blob) cudaFree(e->d_blob);
+    delete e;
+    return -1;
+  }
+  e->X = reinterpret_cast<float*>(ws + w.x);
+  e->Xn = reinterpret_cast<__nv_bfloat16*>(ws + w.xn);
+  e->QKV = reinterpret_cast<__nv_bfloat16*>(ws + w.qkv);
+  e->H = reinterpret_cast<__nv_bfloat16*>(ws + w.h);
+  e->pooled = reinterpret_cast<__nv_bfloat16*>(ws + w.pooled);
+  e->row_idx = reinterpret_cast<int32_t*>(ws + w.rowidx);
+  e->kmask = reinterpret_cast<int32_t*>(ws + w.kmask);
+  cudaError_t ce = cudaMemcpy(e->d_blob, host_blob, nbytes, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess || bind_weights(e) != 0) {
+    if (ce != cudaSuccess) set_last_error("plip_create: weight upload failed: %s", cudaGetErrorString(ce));
+    cudaFree(e->d_blob);
+    cudaFree(ws);
+    delete e;
+    return -1;
+  }
+  *out = e;
+  return 0;
+}
+
+PLIP_API int plip_destroy(plip_engine_t* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  if (e->d_blob) cudaFree(e->d_blob);
+  if (e->X) cudaFree(e->X);  // base of the workspace allocation
+  for (int i = 0; i < 2; ++i) {
+    if (e->d_in[i]) cudaFree(e->d_in[i]);
+    if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
+    if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+    if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+  }
+  if (e->d_out) cudaFree(e->d_out);
+  if (e->d_aux) cudaFree(e->d_aux);
+  if (e->s_compute) cudaStreamDestroy(e->s_compute);
+  if (e->s_copy) cudaStreamDestroy(e->s_copy);
+  delete e;
+  return 0;
+}
+
+PLIP_API float plip_logit_scale_exp(const plip_engine_t* e) { return e ? e->logit_scale_exp : 0.f; }
+PLIP_API int plip_max_micro_batch(const plip_engine_t* e) { return e ? e->max_mb : 0; }
+
+PLIP_API int plip_encode_images(plip_engine_t* e, const void* pixels_dev, int pixel_format, int64_t n,
+                                float* out_dev, int normalize, void* stream) {
+  PLIP_REQUIRE(e && pixels_dev && out_dev, "plip_encode_images: null argument");
+  PLIP_REQUIRE(n > 0, "plip_encode_images: n must be positive (got %lld)", (long long)n);
+  PLIP_REQUIRE(pixel_format >= 0 && pixel_format <= 2, "plip_encode_images: unknown pixel format %d", pixel_format);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t pb = pixel_bytes(pixel_format);
+  for (int64_t i = 0; i < n; i += e->max_mb) {
+    const int64_t mb = (n - i < e->max_mb) ? (n - i) : e->max_mb;
+    if (int rc = vision_forward(e, static_cast<const uint8_t*>(pixels_dev) + i * pb, pixel_format, mb,
+                                out_dev + i * kProj, normalize, st)) return rc;
+  }
+  return 0;
+}
+
+PLIP_API int plip_encode_text(plip_engine_t* e, const void* ids_dev, int ids_dtype, const void* attention_mask_dev,
+                              int64_t n, int seq_len, float* out_dev, int normalize, void* stream) {
+  PLIP_REQUIRE(e && ids_dev && out_dev, "plip_encode_text: null argument");
+  PLIP_REQUIRE(n > 0, "plip_encode_text: n must be positive (got %lld)", (long long)n);
+  PLIP_REQUIRE(seq_len >= 1 && seq_len <= kTxtSeq,
+               "Sequence length must be less than max_position_embeddings (got `sequence length`: %d and "
+               "max_position_embeddings: %d)", seq_len, kTxtSeq);  // message mirrors TF:243-247
+  PLIP_REQUIRE(ids_dtype == PLIP_IDS_I32 || ids_dtype == PLIP_IDS_I64, "plip_encode_text: unknown ids dtype %d", ids_dtype);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t isz = ids_dtype == PLIP_IDS_I64 ? 8 : 4;
+  for (int64_t i = 0; i < n; i += e->max_mb) {
+    const int64_t mb = (n - i < e->max_mb) ? (n - i) : e->max_mb;
+    const uint8_t* ids = static_cast<const uint8_t*>(ids_dev) + i * seq_len * isz;
+    const uint8_t* mk = attention_mask_dev ? static_cast<const uint8_t*>(attention_mask_dev) + i * seq_len * isz : nullptr;
+    if (int rc = text_forward(e, ids, ids_dtype, mk, mb, seq_len, out_dev + i * kProj, normalize, st)) return rc;
+  }
+  return 0;
+}
+
+PLIP_API int plip_similarity(const float* img_dev, int64_t n, const float* txt_dev, int64_t m, float scale,
+                             int normalize_img, int normalize_txt, float* logits_dev, int64_t ld_logits,
+                             void* stream) {
+  PLIP_REQUIRE(img_dev && txt_dev && logits_dev, "plip_similarity: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t chunk = 65535LL * 64;  // grid.y limit
+  for (int64_t i = 0; i < n; i += chunk) {
+    const int64_t rows = n - i < chunk ? n - i : chunk;
+    if (int rc = launch_similarity(img_dev + i * kProj, rows, txt_dev, m, scale, normalize_img != 0,
+                                   normalize_txt != 0, logits_dev + i * ld_logits, ld_logits, st)) return rc;
+  }
+  return 0;
+}
+
+PLIP_API int plip_similarity_topk(const float* query_dev, int64_t n, const float* space_dev, int64_t m, float scale,
+                                  int normalize_query, int normalize_space, int k, int32_t* idx_dev, float* val_dev,
+                                  void* stream) {
+  PLIP_REQUIRE(query_dev && space_dev && idx_dev, "plip_similarity_topk: null argument");
+  return launch_similarity_topk(query_dev, n, space_dev, m, scale, normalize_query != 0, normalize_space != 0, k,
+                                idx_dev, val_dev, static_cast<cudaStream_t>(stream));
+}
+
+PLIP_API int plip_l2_normalize(float* x_dev, int64_t n, int dim, void* stream) {
+  PLIP_REQUIRE(x_dev, "plip_l2_normalize: null argument");
+  return launch_l2_normalize(x_dev, n, dim, static_cast<cudaStream_t>(stream));
+}
+
+// ---- host-buffer path ---------------------------------------------------------------------------
+PLIP_API int plip_encode_images_host(plip_engine_t* e, const void* pixels_host, int pixel_format, int64_t n,
+                                     float* out_host, int normalize) {
+  PLIP_REQUIRE(e && pixels_host && out_host, "plip_encode_images_host: null argument");
+  PLIP_REQUIRE(n > 0, "plip_encode_images_host: n must be positive (got %lld)", (long long)n);
+  PLIP_REQUIRE(pixel_format >= 0 && pixel_format <= 2, "plip_encode_images_host: unknown pixel format %d", pixel_format);
+  PLIP_CUDA_CHECK(cudaSetDevice(e->device));
+  if (int rc = ensure_host_path(e)) return rc;
+  const size_t pb = pixel_bytes(pixel_format);
+  const int64_t chunk = e->max_mb;
+  const size_t in_bytes = (size_t)(n < chunk ? n : chunk) * pb;
+  if (e->d_in_bytes < in_bytes) {
+    size_t have0 = e->d_in_bytes, have1 = e->d_in_bytes;
+    if (int rc = grow_dev(&e->d_in[0], &have0, in_bytes)) return rc;
+    if (int rc = grow_dev(&e->d_in[1], &have1, in_bytes)) return rc;
+    e->d_in_bytes = in_bytes;
+  }
+  if (int rc = grow_dev(reinterpret_cast<void**>(&e->d_out), &e->d_out_bytes, (size_t)n * kProj * 4)) return rc;
+  const bool pinned = is_pinned(pixels_host);
+  if (!pinned && e->h_stage_bytes < in_bytes) {
+    for (int i = 0; i < 2; ++i) {
+      if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
+      e->h_stage[i] = nullptr;
+      PLIP_CUDA_CHECK(cudaMallocHost(&e->h_stage[i], in_bytes));
+    }
+    e->h_stage_bytes = in_bytes;
+  }
+  int64_t ci = 0;
+  for (int64_t i = 0; i < n; i += chunk, ++ci) {
+    const int b = (int)(ci & 1);
+    const int64_t mb = (n - i < chunk) ? (n - i) : chunk;
+    const uint8_t* src = static_cast<const uint8_t*>(pixels_host) + (size_t)i * pb;
+    if (ci >= 2) PLIP_CUDA_CHECK(cudaStreamWaitEvent(e->s_copy, e->ev_done[b], 0));  // device buffer b consumed
+    if (!pinned) {
+      if (ci >= 2) PLIP_CUDA_CHECK(cudaEventSynchronize(e->ev_copied[b]));  // staging buffer b drained
+      memcpy(e->h_stage[b], src, (size_t)mb * pb);
+      src = static_cast<const uint8_t*>(e->h_stage[b]);
+    }
+    PLIP_CUDA_CHECK(cudaMemcpyAsync(e->d_in[b], src, (size_t)mb * pb, cudaMemcpyHostToDevice, e->s_copy));
+    PLIP_CUDA_CHECK(cudaEventRecord(e->ev_copied[b], e->s_copy));
+    PLIP_CUDA_CHECK(cudaStreamWaitEvent(e->s_compute, e->ev_copied[b], 0));
+    if (int rc = vision_forward(e, e->d_in[b], pixel_format, mb, e->d_out + i * kProj, normalize, e->s_compute)) return rc;
+    PLIP_CUDA_CHECK(cudaEventRecord(e->ev_done[b], e->s_compute));
+  }
+  PLIP_CUDA_CHECK(cudaMemcpyAsync(out_host, e->d_out, (size_t)n * kProj * 4, cudaMemcpyDeviceToHost, e->s_compute));
+  PLIP_CUDA_CHECK(cudaStreamSynchronize(e->s_compute));
+  return 0;
+}
+
+PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int ids_dtype, const void* attention_mask_host,
+                                   int64_t n, int seq_len, float* out_host, int normalize) {
+  PLIP_REQUIRE(e && ids_host && out_host, "plip_encode_text_host: null argument");
+  PLIP_REQUIRE(n > 0, "plip_encode_text_host: n must be positive (got %lld)", (long long)n);
+  PLIP_REQUIRE(seq_len >= 1 && seq_len <= kTxtSeq, "plip_encode_text_host: seq_len %d out of [1,77]", seq_len);
+  PLIP_REQUIRE(ids_dtype == PLIP_IDS_I32 || ids_dtype == PLIP_IDS_I64, "plip_encode_text_host: unknown ids dtype %d", ids_dtype);
+  PLIP_CUDA_CHECK(cudaSetDevice(e->device));
+  if (int rc = ensure_host_path(e)) return rc;
+  const size_t isz = ids_dtype == PLIP_IDS_I64 ? 8 : 4;
+  const size_t ib = (size_t)n * seq_len * isz;
+  const size_t ib_al = (ib + 255) & ~(size_t)255;
+  if (int rc = grow_dev(&e->d_aux, &e->d_aux_bytes, 2 * ib_al)) return rc;
+  if (int rc = grow_dev(reinterpret_cast<void**>(&e->d_out), &e->d_out_bytes, (size_t)n * kProj * 4)) return rc;
+  uint8_t* d_ids = static_cast<uint8_t*>(e->d_aux);
+  uint8_t* d_mask = attention_mask_host ? d_ids + ib_al : nullptr;
+  PLIP_CUDA_CHECK(cudaMemcpyAsync(d_ids, ids_host, ib, cudaMemcpyHostToDevice, e->s_compute));
+  if (d_mask) PLIP_CUDA_CHECK(cudaMemcpyAsync(d_mask, attention_mask_host, ib, cudaMemcpyHostToDevice, e->s_compute));
+  if (int rc = plip_encode_text(e, d_ids, ids_dtype, d_mask, n, seq_len, e->d_out, normalize, e->s_compute)) return rc;
+  PLIP_CUDA_CHECK(cudaMemcpyAsync(out_host, e->d_out, (size_t)n * kProj * 4, cudaMemcpyDeviceToHost, e->s_compute));
+  PLIP_CUDA_CHECK(cudaStreamSynchronize(e->s_compute));
+  return 0;
+}
+
+// ---- per-kernel test hooks ------------------------------------------------------------------------
+PLIP_API int plip_dbg_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K,
+                           const float* bias, void* out, int ldo, const float* pos, int epilogue, int cta_group,
+                           int block_n, void* stream) {
+  GemmArgs g;
+  g.A = static_cast<const __nv_bfloat16*>(A_bf16); g.lda = lda;
+  g.W = static_cast<const __nv_bfloat16*>(W_bf16); g.ldw = ldw;
+  g.M = M; g.N = N; g.K = K;
+  g.bias = bias; g.out = out; g.ldo = ldo; g.pos = pos; g.epi = epilogue;
+  g.force_cg = cta_group; g.force_bn = block_n;
+  return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+PLIP_API int plip_dbg_layernorm(const float* x, int64_t rows, int dim, int64_t in_row_stride, const float* gamma,
+                                const float* beta, float* out_f32, void* out_bf16, void* stream) {
+  return launch_layernorm(x, nullptr, in_row_stride, rows, dim, gamma, beta, out_f32,
+                          static_cast<__nv_bfloat16*>(out_bf16), static_cast<cudaStream_t>(stream));
+}
+
+PLIP_API int plip_dbg_attention(const void* qkv_bf16, int64_t n_seq, int seq_len, int heads, int causal,
+                                const int32_t* key_mask, void* out_bf16, void* stream) {
+  return launch_attention(static_cast<const __nv_bfloat16*>(qkv_bf16), n_seq, seq_len, heads, causal != 0, key_mask,
+                          static_cast<__nv_bfloat16*>(out_bf16), static_cast<cudaStream_t>(stream));
+}
+
+PLIP_API int plip_dbg_im2col(const void* pixels, int pixel_format, int64_t n, void* out_bf16, void* stream) {
+  return launch_im2col(pixels, pixel_format, n, static_cast<__nv_bfloat16*>(out_bf16), static_cast<cudaStream_t>(stream));
+}
+
+PLIP_API int plip_dbg_hidden_states(plip_engine_t* e, int tower, const void* input_dev, int input_format,
+                                    const void* attention_mask_dev, int64_t n, int num_layers, float* hidden_dev,
+                                    void* stream) {
+  PLIP_REQUIRE(e && input_dev && hidden_dev, "plip_dbg_hidden_states: null argument");
+  PLIP_REQUIRE(n > 0 && n <= e->max_mb, "plip_dbg_hidden_states: n=%lld must be in [1, max_micro_batch]", (long long)n);
+  PLIP_REQUIRE(num_layers >= 0 && num_layers <= kLayers, "plip_dbg_hidden_states: num_layers %d", num_layers);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t bytes;
+  if (tower == 0) {
+    if (int rc = vision_trunk(e, input_dev, input_format, n, num_layers, st)) return rc;
+    bytes = (size_t)n * kVisSeq * kVisDim * 4;
+  } else {
+    if (int rc = text_trunk(e, input_dev, input_format, attention_mask_dev, n, kTxtSeq, num_layers, st)) return rc;
+    bytes = (size_t)n * kTxtSeq * kTxtDim * 4;
+  }
+  PLIP_CUDA_CHECK(cudaMemcpyAsync(hidden_dev, e->X, bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+}  // extern "C"

@@ -39,10 +39,11 @@ struct Cfg {
   static constexpr int LOAD_N = BN / CG;  // W rows staged by each CTA
   static constexpr uint32_t B_STAGE = LOAD_N * BK * 2;
   static constexpr uint32_t STAGE = A_STAGE + B_STAGE;
-  static constexpr int kMaxStages = (227 * 1024 - 1024 - 512) / STAGE;
+  static constexpr uint32_t EPI_BYTES = 4 * 32 * 128 + 2 * BN * 4;  // 4 warp staging blocks + 2 bias tiles
+  static constexpr int kMaxStages = (227 * 1024 - 1024 - 512 - EPI_BYTES) / STAGE;
   static constexpr int STAGES = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE + 1024 + 512;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE + EPI_BYTES + 1024 + 512;
 };
 
 struct GemmDev {
@@ -53,75 +54,125 @@ struct GemmDev {
   const float* pos;
 };
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_store(const GemmDev& p, int row, int col0,
-                                               const uint32_t (&v)[32]) {
-  if (row >= p.M) return;
-  float f[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+// ---- epilogue ---------------------------------------------------------------------------------
+// A thread owns one accumulator row (TMEM lane).  Writing rows straight to global memory makes every
+// warp-level store touch 32 different cache lines; instead each warp stages a [32 rows x 128 B] block
+// in shared memory (16-byte chunks XOR-swizzled by row, the SWIZZLE_128B pattern) and reads it back
+// with 8 lanes per row, so each global access covers 4 rows x 128 contiguous bytes.
+constexpr uint32_t kEpiStageBytes = 32 * 128;  // per epilogue warp
 
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 b = __ldg(b4 + i);
-      f[4 * i + 0] += b.x;
-      f[4 * i + 1] += b.y;
-      f[4 * i + 2] += b.z;
-      f[4 * i + 3] += b.w;
-    }
-  }
-  if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
-  }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-    uint4* o4 = reinterpret_cast<uint4*>(o);
+// acc (+ bias from the smem bias tile) for 32 consecutive columns of this thread's row.
+template <bool HAS_BIAS>
+__device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, float (&f)[32]) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+  tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
-      u.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
-      u.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
-      u.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
-      o4[i] = u;
+  for (int i = 0; i < 8; ++i) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (HAS_BIAS) b = ld_shared_f4(bias_smem + 16 * i);  // broadcast read
+    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
+    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
+    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+  }
+}
+
+// One accumulator tile (this warp's 32 rows x BN columns) -> global memory.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_row_base, uint32_t stage_smem,
+                                              uint32_t bias_smem, int row_base, int col_base, int lane) {
+  constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32);
+  constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
+  const uint32_t my_row = stage_smem + lane * 128;
+  const int sw = lane & 7;
+  const int rb_row = lane >> 3;  // read-back: row within a group of 4
+  const int rb_chunk = lane & 7;  // read-back: 16-byte chunk of the row
+
+  if constexpr (OUT_BF16) {
+#pragma unroll 1
+    for (int blk = 0; blk < BN / 64; ++blk) {
+      // 64 columns -> 128 B of bf16 per row
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float f[32];
+        load_acc32<HAS_BIAS>(tmem_row_base + blk * 64 + half * 32, bias_smem + (blk * 64 + half * 32) * 4, f);
+        if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int chunk = half * 4 + c;
+          st_shared_v4(my_row + ((chunk ^ sw) << 4), pack_bf16x2(f[8 * c + 0], f[8 * c + 1]),
+                       pack_bf16x2(f[8 * c + 2], f[8 * c + 3]), pack_bf16x2(f[8 * c + 4], f[8 * c + 5]),
+                       pack_bf16x2(f[8 * c + 6], f[8 * c + 7]));
+        }
+      }
+      __syncwarp();
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + rb_row;
+        const uint4 v = ld_shared_v4(stage_smem + r * 128 + ((rb_chunk ^ (r & 7)) << 4));
+        const int grow = row_base + r;
+        if (grow < p.M)
+          *reinterpret_cast<uint4*>(out + static_cast<size_t>(grow) * p.ldo + col_base + blk * 64 + rb_chunk * 8) = v;
+      }
+      __syncwarp();
     }
-  } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
-    float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                           static_cast<size_t>(row) * p.ldo + col0);
-    float4 r[8];
+  } else {
+#pragma unroll 1
+    for (int blk = 0; blk < BN / 32; ++blk) {
+      // 32 columns -> 128 B of fp32 per row
+      {
+        float f[32];
+        load_acc32<HAS_BIAS>(tmem_row_base + blk * 32, bias_smem + blk * 32 * 4, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = x4[i];
+        for (int c = 0; c < 8; ++c)
+          st_shared_v4(my_row + ((c ^ sw) << 4), __float_as_uint(f[4 * c + 0]), __float_as_uint(f[4 * c + 1]),
+                       __float_as_uint(f[4 * c + 2]), __float_as_uint(f[4 * c + 3]));
+      }
+      __syncwarp();
+      float* out = reinterpret_cast<float*>(p.out);
+      const int col = col_base + blk * 32 + rb_chunk * 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      r[i].x += f[4 * i + 0];
-      r[i].y += f[4 * i + 1];
-      r[i].z += f[4 * i + 2];
-      r[i].w += f[4 * i + 3];
-      x4[i] = r[i];
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + rb_row;
+        float4 v = ld_shared_f4(stage_smem + r * 128 + ((rb_chunk ^ (r & 7)) << 4));
+        const int grow = row_base + r;
+        if (grow < p.M) {
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            float4* x4 = reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldo + col);
+            const float4 x = *x4;
+            *x4 = make_float4(x.x + v.x, x.y + v.y, x.z + v.z, x.w + v.w);
+          } else if constexpr (EPI == EPI_PATCH_F32) {
+            const int b = grow / kPatches;
+            const int pp = grow - b * kPatches;
+            const float4 q = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pp) * p.N + col));
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(b * kVisSeq + 1 + pp) * p.ldo + col) =
+                make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
+          } else {
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldo + col) = v;
+          }
+        }
+      }
+      __syncwarp();
     }
-  } else if constexpr (EPI == EPI_PATCH_F32) {
-    const int b = row / kPatches;
-    const int pp = row - b * kPatches;
-    const float4* pos4 =
-        reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + pp) * p.N + col0);
-    float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                           static_cast<size_t>(b * kVisSeq + 1 + pp) * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 q = __ldg(pos4 + i);
-      x4[i] = make_float4(f[4 * i + 0] + q.x, f[4 * i + 1] + q.y, f[4 * i + 2] + q.z,
-                          f[4 * i + 3] + q.w);
-    }
-  } else {  // EPI_F32
-    float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                           static_cast<size_t>(row) * p.ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      x4[i] = make_float4(f[4 * i + 0], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
   }
 }
 
@@ -134,7 +185,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * C::STAGE;
+  const uint32_t epi_base = smem_base + STAGES * C::STAGE;   // 1024-aligned: 4 x 4 KB staging blocks
+  const uint32_t bias_base = epi_base + 4 * kEpiStageBytes;  // 2 x BN floats
+  const uint32_t bar_base = smem_base + STAGES * C::STAGE + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -232,22 +285,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32);
     const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int etid = threadIdx.x - 128;
     int a = 0;
     uint32_t aph = 0;
     for (int t = tile0; t < num_tiles; t += tile_step) {
       const int m_blk = t / num_n_blk, n_blk = t - m_blk * num_n_blk;
+      if constexpr (HAS_BIAS) {
+        // bias tile for this accumulator stage (its previous readers are two tiles behind us)
+        float* bs = reinterpret_cast<float*>(smem_raw + (bias_base - smem_raw_u32)) + a * BN;
+        for (int i = etid; i < BN; i += 128) bs[i] = __ldg(p.bias + n_blk * BN + i);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
-      const int row = m_blk * BM * CG + cta_rank * BM + q * 32 + lane;
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tbase + c * 32, v);
-        tmem_ld_wait();
-        epilogue_store<EPI>(p, row, n_blk * BN + c * 32, v);
-      }
+      const int row_base = m_blk * BM * CG + cta_rank * BM + q * 32;
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
+      epilogue_tile<BN, EPI>(p, trow, epi_base + q * kEpiStageBytes, bias_base + a * BN * 4, row_base, n_blk * BN, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -262,6 +317,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
 
 int num_sms() {
@@ -280,9 +340,31 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   using C = Cfg<CG, BN>;
   auto kern = gemm_kernel<CG, BN, EPI>;
   static bool configured = false;
+  static int max_groups = 0;  // co-resident CTAs (CG == 1) or CTA pairs (CG == 2) for this kernel
   if (!configured) {
     PLIP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM_BYTES));
+    max_groups = num_sms() / CG;
+    if (CG == 2) {
+      // A persistent grid must be fully co-resident: ask how many CTA pairs fit at once (SM pairs
+      // must share a TPC, so this can be below num_sms / 2).
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(num_sms());
+      q.blockDim = dim3(kThreads);
+      q.dynamicSmemBytes = C::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CG; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int n_clusters = 0;
+      PLIP_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q));
+      if (n_clusters > 0 && n_clusters < max_groups) max_groups = n_clusters;
+    }
+    const int env_groups = env_int("PLIP_GEMM_GROUPS", 0);
+    if (env_groups > 0) max_groups = env_groups;
+    if (env_int("PLIP_DEBUG", 0))
+      fprintf(stderr, "plip_b200: gemm<cg=%d,bn=%d,epi=%d> stages=%d smem=%u max_groups=%d\n", CG, BN, EPI,
+              C::STAGES, C::SMEM_BYTES, max_groups);
     configured = true;
   }
   CUtensorMap tmA, tmB;
@@ -294,7 +376,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   p.bias = g.bias; p.out = g.out; p.ldo = g.ldo; p.pos = g.pos;
 
   const int num_tiles = ((g.M + BM * CG - 1) / (BM * CG)) * (g.N / BN);
-  int groups = num_sms() / CG;
+  int groups = max_groups;
   if (groups > num_tiles) groups = num_tiles;
 
   cudaLaunchConfig_t cfg = {};
@@ -324,11 +406,6 @@ int launch_epi(const GemmArgs& g, cudaStream_t stream) {
     case EPI_F32: return launch_inst<CG, BN, EPI_F32>(g, stream);
     default: set_last_error("launch_gemm: bad epilogue %d", g.epi); return -2;
   }
-}
-
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
 }
 
 }  // namespace

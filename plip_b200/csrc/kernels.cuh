@@ -1,0 +1,32 @@
+// plip_b200 — host-side launchers of the non-GEMM kernels.
+#pragma once
+#include "plip_b200.h"
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace plip {
+
+// elementwise.cu
+int launch_im2col(const void* pixels, int fmt, int64_t n, __nv_bfloat16* out, cudaStream_t st);
+int launch_layernorm(const float* x, const int32_t* row_index, int64_t in_row_stride, int64_t rows, int dim,
+                     const float* gamma, const float* beta, float* out_f32, __nv_bfloat16* out_bf16,
+                     cudaStream_t st);
+int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, const float* tok, const float* pos,
+                      float* x, int32_t* eos_rows, int eos_id, cudaStream_t st);
+int launch_mask_to_i32(const void* mask, int dtype, int64_t count, int32_t* out, cudaStream_t st);
+int launch_cls_rows(const float* cls, const float* pos, int64_t n, float* x, cudaStream_t st);
+int launch_l2_normalize(float* x, int64_t rows, int dim, cudaStream_t st);
+
+// attention.cu: softmax(q k^T [+causal/padding mask]) v per (sequence, head); q pre-scaled by dh^-0.5.
+// qkv: bf16 [n_seq*seq_len, 3*heads*64]; key_mask: optional int32 [n_seq, seq_len] (0 = masked key).
+int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int heads, bool causal,
+                     const int32_t* key_mask, __nv_bfloat16* out, cudaStream_t st);
+
+// similarity.cu
+int launch_similarity(const float* a, int64_t n, const float* b, int64_t m, float scale, bool norm_a, bool norm_b,
+                      float* out, int64_t ldo, cudaStream_t st);
+int launch_similarity_topk(const float* q, int64_t n, const float* s, int64_t m, float scale, bool norm_q,
+                           bool norm_s, int k, int32_t* idx, float* val, cudaStream_t st);
+
+}  // namespace plip

@@ -1,0 +1,231 @@
+"""Python handle on the CUDA engine: device memory and streams come from torch, compute from the
+C ABI (``libplip_b200.so``).  There is no fallback path: a missing library or GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Mapping, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .weights import pack_state_dict
+
+PIX_F32_NCHW, PIX_BF16_NCHW, PIX_U8_NHWC = 0, 1, 2
+IDS_I32, IDS_I64 = 0, 1
+EMBED_DIM = 512
+IMAGE_SIZE = 224
+MAX_TEXT_LEN = 77
+
+
+def _pixel_format(t: Union[torch.Tensor, np.ndarray]) -> int:
+    """Validate an image batch and return its C-ABI pixel format (error text mirrors TF:204-207)."""
+    shape, dtype = tuple(t.shape), t.dtype
+    if dtype in (torch.uint8, np.dtype("uint8")):
+        if len(shape) != 4 or shape[3] != 3:
+            raise ValueError(f"uint8 images must be [n,224,224,3] (NHWC), got {shape}")
+        if shape[1] != IMAGE_SIZE or shape[2] != IMAGE_SIZE:
+            raise ValueError(f"Input image size ({shape[1]}*{shape[2]}) doesn't match model (224*224).")
+        return PIX_U8_NHWC
+    if len(shape) != 4 or shape[1] != 3:
+        raise ValueError(f"pixel_values must be [n,3,224,224], got {shape}")
+    if shape[2] != IMAGE_SIZE or shape[3] != IMAGE_SIZE:
+        raise ValueError(f"Input image size ({shape[2]}*{shape[3]}) doesn't match model (224*224).")
+    if dtype in (torch.float32, np.dtype("float32")):
+        return PIX_F32_NCHW
+    if dtype == torch.bfloat16:
+        return PIX_BF16_NCHW
+    raise TypeError(f"unsupported pixel dtype {dtype} (float32, bfloat16 or uint8)")
+
+
+def _ids_dtype(dtype) -> int:
+    if dtype in (torch.int64, np.dtype("int64")):
+        return IDS_I64
+    if dtype in (torch.int32, np.dtype("int32")):
+        return IDS_I32
+    raise TypeError(f"input_ids must be int32 or int64, got {dtype}")
+
+
+def _check_ids(input_ids, attention_mask) -> Tuple[int, int]:
+    if len(input_ids.shape) != 2:
+        raise ValueError(f"input_ids must be [n, seq_len], got {tuple(input_ids.shape)}")
+    n, s = int(input_ids.shape[0]), int(input_ids.shape[1])
+    if s > MAX_TEXT_LEN:
+        raise ValueError(
+            "Sequence length must be less than max_position_embeddings (got `sequence length`: "
+            f"{s} and max_position_embeddings: {MAX_TEXT_LEN}")  # TF:243-247
+    if attention_mask is not None and tuple(attention_mask.shape) != (n, s):
+        raise ValueError(f"attention_mask shape {tuple(attention_mask.shape)} != input_ids shape {(n, s)}")
+    return n, s
+
+
+class Engine:
+    """One engine per CUDA device: packed bf16/fp32 weights + workspace for ``max_micro_batch``."""
+
+    def __init__(self, state_dict: Mapping[str, torch.Tensor], device: Union[int, str, torch.device, None] = None,
+                 max_micro_batch: int = 1024):
+        if not torch.cuda.is_available():
+            raise RuntimeError("plip_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._L = lib()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"plip_b200 runs on CUDA devices only, got {dev}")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        blob, scale = pack_state_dict(state_dict)
+        self.logit_scale_exp = float(scale)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            torch.cuda.init()
+            check(self._L.plip_create(blob.data_ptr(), blob.numel(), C.c_float(scale), self.device.index,
+                                      int(max_micro_batch), C.byref(h)), "plip_create")
+        self._h = h
+        self.max_micro_batch = int(max_micro_batch)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.plip_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _dev(self, t: torch.Tensor) -> torch.Tensor:
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t.contiguous()
+
+    # ---- device-tensor API -------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_images(self, pixels: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+        """``get_image_features``: ``[n,3,224,224]`` f32/bf16 or ``[n,224,224,3]`` u8 -> ``[n,512]`` f32 (device)."""
+        fmt = _pixel_format(pixels)
+        n = int(pixels.shape[0])
+        if n == 0:
+            return torch.empty(0, EMBED_DIM, device=self.device)
+        pixels = self._dev(pixels)
+        out = torch.empty(n, EMBED_DIM, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self._L.plip_encode_images(self._h, pixels.data_ptr(), fmt, n, out.data_ptr(), int(normalize),
+                                             self._stream()), "plip_encode_images")
+        return out
+
+    @torch.no_grad()
+    def encode_text(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                    normalize: bool = False) -> torch.Tensor:
+        """``get_text_features``: ids ``[n,<=77]`` int32/int64 (+ optional mask) -> ``[n,512]`` f32 (device)."""
+        n, s = _check_ids(input_ids, attention_mask)
+        if n == 0:
+            return torch.empty(0, EMBED_DIM, device=self.device)
+        idt = _ids_dtype(input_ids.dtype)
+        ids = self._dev(input_ids)
+        mask = None
+        if attention_mask is not None:
+            mask = self._dev(attention_mask.to(input_ids.dtype))
+        out = torch.empty(n, EMBED_DIM, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self._L.plip_encode_text(self._h, ids.data_ptr(), idt, mask.data_ptr() if mask is not None else None,
+                                           n, s, out.data_ptr(), int(normalize), self._stream()), "plip_encode_text")
+        return out
+
+    @torch.no_grad()
+    def similarity(self, image_embeds: torch.Tensor, text_embeds: torch.Tensor, scale: Optional[float] = None,
+                   normalize_image: bool = True, normalize_text: bool = True) -> torch.Tensor:
+        """``logits_per_image[n,m] = scale * norm(image) @ norm(text).T`` (TF:923-930), fp32."""
+        a = self._dev(image_embeds.to(torch.float32))
+        b = self._dev(text_embeds.to(torch.float32))
+        if a.shape[-1] != EMBED_DIM or b.shape[-1] != EMBED_DIM:
+            raise ValueError("embeddings must have 512 columns")
+        n, m = int(a.shape[0]), int(b.shape[0])
+        ld = (m + 3) // 4 * 4
+        out = torch.empty(n, ld, device=self.device, dtype=torch.float32)
+        if n == 0 or m == 0:
+            return out[:, :m]
+        s = self.logit_scale_exp if scale is None else float(scale)
+        with torch.cuda.device(self.device):
+            check(self._L.plip_similarity(a.data_ptr(), n, b.data_ptr(), m, C.c_float(s), int(normalize_image),
+                                          int(normalize_text), out.data_ptr(), ld, self._stream()), "plip_similarity")
+        return out[:, :m]
+
+    @torch.no_grad()
+    def similarity_topk(self, query: torch.Tensor, space: torch.Tensor, k: int, scale: float = 1.0,
+                        normalize_query: bool = True, normalize_space: bool = False):
+        """Fused scores + top-k over ``space`` rows: returns ``(idx int32 [n,k], val f32 [n,k])``, descending."""
+        q = self._dev(query.to(torch.float32))
+        s = self._dev(space.to(torch.float32))
+        n = int(q.shape[0])
+        idx = torch.empty(n, k, device=self.device, dtype=torch.int32)
+        val = torch.empty(n, k, device=self.device, dtype=torch.float32)
+        if n == 0:
+            return idx, val
+        with torch.cuda.device(self.device):
+            check(self._L.plip_similarity_topk(q.data_ptr(), n, s.data_ptr(), int(s.shape[0]), C.c_float(scale),
+                                               int(normalize_query), int(normalize_space), int(k), idx.data_ptr(),
+                                               val.data_ptr(), self._stream()), "plip_similarity_topk")
+        return idx, val
+
+    @torch.no_grad()
+    def l2_normalize_(self, x: torch.Tensor) -> torch.Tensor:
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        if x.shape[0]:
+            with torch.cuda.device(self.device):
+                check(self._L.plip_l2_normalize(x.data_ptr(), int(x.shape[0]), int(x.shape[1]), self._stream()),
+                      "plip_l2_normalize")
+        return x
+
+    # ---- host-buffer API (copies inside the call) ------------------------------------------------
+    def encode_images_host(self, pixels: Union[np.ndarray, torch.Tensor], normalize: bool = False,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host array in, host ``[n,512]`` f32 tensor out; H2D/D2H pipelined inside the C call."""
+        fmt = _pixel_format(pixels)
+        t = torch.from_numpy(np.ascontiguousarray(pixels)) if isinstance(pixels, np.ndarray) else pixels.contiguous()
+        assert not t.is_cuda, "encode_images_host takes host memory; use encode_images for device tensors"
+        n = int(t.shape[0])
+        if out is None:
+            out = torch.empty(n, EMBED_DIM, dtype=torch.float32)
+        if n:
+            check(self._L.plip_encode_images_host(self._h, t.data_ptr(), fmt, n, out.data_ptr(), int(normalize)),
+                  "plip_encode_images_host")
+        return out
+
+    def encode_text_host(self, input_ids: Union[np.ndarray, torch.Tensor], attention_mask=None,
+                         normalize: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        ids = torch.from_numpy(np.ascontiguousarray(input_ids)) if isinstance(input_ids, np.ndarray) else input_ids.contiguous()
+        n, s = _check_ids(ids, attention_mask)
+        idt = _ids_dtype(ids.dtype)
+        mask = None
+        if attention_mask is not None:
+            mask = (torch.from_numpy(np.ascontiguousarray(attention_mask)) if isinstance(attention_mask, np.ndarray)
+                    else attention_mask).to(ids.dtype).contiguous()
+        if out is None:
+            out = torch.empty(n, EMBED_DIM, dtype=torch.float32)
+        if n:
+            check(self._L.plip_encode_text_host(self._h, ids.data_ptr(), idt, mask.data_ptr() if mask is not None else None,
+                                                n, s, out.data_ptr(), int(normalize)), "plip_encode_text_host")
+        return out
+
+    # ---- test hook ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def hidden_states(self, tower: str, inputs: torch.Tensor, num_layers: int,
+                      attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Residual stream after ``num_layers`` encoder layers (fp32), for layer-wise parity tests."""
+        x = self._dev(inputs)
+        n = int(x.shape[0])
+        if tower == "vision":
+            fmt, t, shape = _pixel_format(x), 0, (n, 50, 768)
+        else:
+            fmt, t, shape = _ids_dtype(x.dtype), 1, (n, 77, 512)
+            assert x.shape[1] == 77
+        mask = self._dev(attention_mask.to(x.dtype)) if attention_mask is not None else None
+        out = torch.empty(shape, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self._L.plip_dbg_hidden_states(self._h, t, x.data_ptr(), fmt,
+                                                 mask.data_ptr() if mask is not None else None, n, int(num_layers),
+                                                 out.data_ptr(), self._stream()), "plip_dbg_hidden_states")
+        return out
