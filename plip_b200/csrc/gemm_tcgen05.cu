@@ -139,6 +139,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
 #pragma unroll 1
     for (int blk = 0; blk < BN / 32; ++blk) {
       // 32 columns -> 128 B of fp32 per row
+      const int col = col_base + blk * 32 + rb_chunk * 4;
+      float* out = reinterpret_cast<float*>(p.out);
+      // Residual rows are fetched before the TMEM load / staging so their DRAM latency overlaps it
+      // (issued back to back: a load->add->store chain per row serialises 8 round trips per block).
+      float4 xr[8];
+      if constexpr (EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int grow = row_base + i * 4 + rb_row;
+          xr[i] = (grow < p.M) ? *reinterpret_cast<const float4*>(out + static_cast<size_t>(grow) * p.ldo + col)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       {
         float f[32];
         load_acc32<HAS_BIAS>(tmem_row_base + blk * 32, bias_smem + blk * 32 * 4, f);
@@ -148,8 +161,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
                        __float_as_uint(f[4 * c + 2]), __float_as_uint(f[4 * c + 3]));
       }
       __syncwarp();
-      float* out = reinterpret_cast<float*>(p.out);
-      const int col = col_base + blk * 32 + rb_chunk * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = i * 4 + rb_row;
@@ -157,9 +168,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
         const int grow = row_base + r;
         if (grow < p.M) {
           if constexpr (EPI == EPI_BIAS_RESID_F32) {
-            float4* x4 = reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldo + col);
-            const float4 x = *x4;
-            *x4 = make_float4(x.x + v.x, x.y + v.y, x.z + v.z, x.w + v.w);
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldo + col) =
+                make_float4(xr[i].x + v.x, xr[i].y + v.y, xr[i].z + v.z, xr[i].w + v.w);
           } else if constexpr (EPI == EPI_PATCH_F32) {
             const int b = grow / kPatches;
             const int pp = grow - b * kPatches;
@@ -298,9 +308,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int i = etid; i < BN; i += 128) bs[i] = __ldg(p.bias + n_blk * BN + i);
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      const int row_base = m_blk * BM * CG + cta_rank * BM + q * 32;
+      if constexpr (EPI == EPI_BIAS_RESID_F32) {
+        // pull this warp's [32 rows x BN] slice of the residual stream into L2 while the MMAs run
+        const float* xin = reinterpret_cast<const float*>(p.out);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int grow = row_base + j * 4 + (lane >> 3);
+          if (grow < p.M) {
+#pragma unroll
+            for (int c = 0; c < BN / 256 + (BN % 256 != 0); ++c) {
+              const float* ptr = xin + static_cast<size_t>(grow) * p.ldo + n_blk * BN + c * 256 + (lane & 7) * 32;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            }
+          }
+        }
+      }
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
-      const int row_base = m_blk * BM * CG + cta_rank * BM + q * 32;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
       epilogue_tile<BN, EPI>(p, trow, epi_base + q * kEpiStageBytes, bias_base + a * BN * 4, row_base, n_blk * BN, lane);
       tc_fence_before();

@@ -1,0 +1,107 @@
+"""Drop-in for ``reproducibility/embedders`` (``plip.py`` ``CLIPEmbedder``, ``factory.py``, ``abst.py``).
+
+``CLIPEmbedder`` keeps the reference's constructor ``(model, preprocess, name, backbone)`` and its four methods
+(``image_embedder``, ``text_embedder``, ``embed_images``, ``embed_text``; ``embedders/plip.py:11-75``) and returns
+**L2-normalised** float32 numpy embeddings like the reference does (``:53,:73``).  ``model`` is any object with
+the OpenAI-clip surface ``encode_image`` / ``encode_text`` returning torch tensors — here a
+:class:`plip_b200.modeling.PlipCLIPModel` — so the reference's evaluation scripts run unchanged on top of it.
+The ``.npy`` embedding cache of the reference (``utils/cacher.py``) is a disk cache orthogonal to compute and is
+out of scope: ``image_embedder`` / ``text_embedder`` always compute.
+"""
+from __future__ import annotations
+
+import os
+from abc import ABC, abstractmethod
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .modeling import PlipCLIPModel
+from .preprocess import chunks, to_uint8_tiles
+
+
+class AbstractEmbedder(ABC):
+    """``reproducibility/embedders/abst.py:3-11``."""
+
+    @abstractmethod
+    def image_embedder(self, list_of_images, device="cuda", num_workers=1, batch_size=32, additional_cache_name=""):
+        ...
+
+    @abstractmethod
+    def text_embedder(self, list_of_labels, device="cuda", num_workers=1, batch_size=32, additional_cache_name=""):
+        ...
+
+
+def _default_tokenize() -> Optional[Callable]:
+    try:
+        import clip  # OpenAI clip package (not installed in this image)
+        return lambda captions: clip.tokenize(captions, truncate=True)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+class CLIPEmbedder(AbstractEmbedder):
+
+    def __init__(self, model, preprocess, name, backbone, tokenize: Optional[Callable] = None):
+        self.model = model
+        self.preprocess = preprocess  # kept for API parity; tiles are prepared by plip_b200.preprocess
+        self.name = name
+        self.backbone = backbone
+        self.tokenize = tokenize or _default_tokenize()
+
+    def image_embedder(self, list_of_images, device="cuda", num_workers=1, batch_size=32, additional_cache_name=""):
+        return self.embed_images(list_of_images, device=device, num_workers=num_workers, batch_size=batch_size)
+
+    def text_embedder(self, list_of_labels, device="cuda", num_workers=1, batch_size=32, additional_cache_name=""):
+        return self.embed_text(list_of_labels, device=device, num_workers=num_workers, batch_size=batch_size)
+
+    def embed_images(self, list_of_images: Sequence, device="cuda", num_workers=1, batch_size=32) -> np.ndarray:
+        """``embedders/plip.py:37-54``: paths / PIL images -> normalised ``[N,512]`` float32."""
+        outs: List[torch.Tensor] = []
+        eng = getattr(self.model, "engine", None)
+        for chunk in chunks(list(list_of_images), max(int(batch_size), 256)):
+            tiles = to_uint8_tiles(chunk)
+            if eng is not None:
+                outs.append(eng.encode_images_host(tiles, normalize=True))
+            else:  # any OpenAI-clip-like model
+                t = torch.from_numpy(tiles).to(device)
+                e = self.model.encode_image(t).detach().float().cpu()
+                outs.append(e / e.norm(dim=1, keepdim=True))
+        return torch.cat(outs, dim=0).numpy()
+
+    def embed_text(self, list_of_labels: Sequence, device="cuda", num_workers=1, batch_size=32) -> np.ndarray:
+        """``embedders/plip.py:56-75``: captions (or pre-tokenised id rows) -> normalised ``[N,512]`` float32."""
+        labels = list(list_of_labels)
+        if len(labels) and not isinstance(labels[0], str):
+            idx = torch.as_tensor(np.asarray(labels))
+        else:
+            if self.tokenize is None:
+                raise RuntimeError("no tokenizer available (the `clip` package is not installed): pass a "
+                                   "`tokenize` callable or pre-tokenised id rows")
+            idx = self.tokenize(labels)
+        outs = []
+        for chunk in chunks(idx, max(int(batch_size), 1024)):
+            e = self.model.encode_text(chunk.to(device)).detach().float()
+            outs.append((e / e.norm(dim=1, keepdim=True)).cpu())
+        return torch.cat(outs, dim=0).numpy()
+
+
+class EmbedderFactory:
+    """``reproducibility/embedders/factory.py:15-32`` for the ``plip`` / ``clip`` branches: ``args.model_name``
+    selects the flavour, ``args.backbone`` is the path of an OpenAI-clip (or HF) state dict saved with ``torch.save``.
+    The ``mudipath`` DenseNet baseline is a different model family and out of scope."""
+
+    def factory(self, args):
+        name, path = args.model_name, args.backbone
+        arch = os.environ.get("PC_CLIP_ARCH", "ViT-B/32")
+        if arch != "ViT-B/32":
+            raise ValueError(f"plip_b200 implements ViT-B/32 only (PC_CLIP_ARCH={arch!r})")
+        if name in ("plip", "clip"):
+            sd = torch.load(path, map_location="cpu")
+            if isinstance(sd, dict) and "state_dict" in sd:
+                sd = sd["state_dict"]
+            model = PlipCLIPModel(sd)
+            model.eval()
+            return CLIPEmbedder(model, None, name, path)
+        raise ValueError(f"unsupported embedder {name!r} (plip / clip)")

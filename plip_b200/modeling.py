@@ -1,0 +1,124 @@
+"""Drop-in for the ``transformers.CLIPModel`` call surface used by the reference.
+
+``PlipCLIPModel`` keeps the three entry points the reference touches —
+``get_image_features`` (reference ``plip.py:50``), ``get_text_features`` (``plip.py:68``) and
+``model(**inputs).logits_per_image`` (``README.md:45-49``; TF:modeling_clip.py:867-944) — and the OpenAI-clip
+``encode_image`` / ``encode_text`` used by ``reproducibility/embedders/plip.py:48,66``.  All compute runs in the
+CUDA engine; outputs are torch tensors on the engine's device, like the HF model's.
+
+Return types follow what the reference code expects (transformers v4 semantics): ``get_*_features`` return
+the ``[n,512]`` tensor itself — the reference calls ``.detach().cpu().numpy()`` on it directly.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Mapping, Optional, Union
+
+import torch
+
+from .engine import Engine
+
+
+@dataclass
+class CLIPOutput:
+    """Fields of ``transformers.models.clip.modeling_clip.CLIPOutput`` (TF:104-135) that the engine produces."""
+
+    logits_per_image: torch.Tensor
+    logits_per_text: torch.Tensor
+    text_embeds: torch.Tensor
+    image_embeds: torch.Tensor
+    loss: Optional[torch.Tensor] = None
+
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+    def keys(self):
+        return ("logits_per_image", "logits_per_text", "text_embeds", "image_embeds")
+
+
+class PlipCLIPModel:
+    """CUDA-engine-backed stand-in for ``CLIPModel`` (ViT-B/32 geometry only, as PLIP ships)."""
+
+    def __init__(self, state_dict: Mapping[str, torch.Tensor], device: Union[int, str, torch.device, None] = None,
+                 max_micro_batch: int = 1024):
+        self.engine = Engine(state_dict, device=device, max_micro_batch=max_micro_batch)
+        self.device = self.engine.device
+        self.training = False
+
+    # ---- construction -------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, name_or_path: str, device=None, max_micro_batch: int = 1024, **hf_kwargs):
+        """Read a HuggingFace CLIP checkpoint (e.g. ``vinid/plip`` or a local directory) on the host and pack
+        it for the engine.  ``transformers`` is only the checkpoint *reader* here; its forward never runs.
+        ``use_auth_token`` (reference ``plip.py:26``) is translated to ``token`` for transformers >= 5."""
+        from transformers import CLIPModel  # host-side weight loading only
+
+        tok = hf_kwargs.pop("use_auth_token", None)
+        if tok is not None:
+            hf_kwargs.setdefault("token", tok)
+        hf = CLIPModel.from_pretrained(name_or_path, **hf_kwargs)
+        cfg = hf.config
+        if (cfg.vision_config.hidden_size, cfg.vision_config.patch_size, cfg.text_config.hidden_size,
+                cfg.projection_dim) != (768, 32, 512, 512):
+            raise ValueError("plip_b200 implements the CLIP ViT-B/32 geometry only (PLIP's architecture)")
+        return cls(hf.state_dict(), device=device, max_micro_batch=max_micro_batch)
+
+    @classmethod
+    def from_openai_state_dict(cls, state_dict, device=None, max_micro_batch: int = 1024):
+        """``clip.load(arch)`` + ``load_state_dict(torch.load(path))`` (``embedders/factory.py:20-27``)."""
+        return cls(state_dict, device=device, max_micro_batch=max_micro_batch)
+
+    # ---- nn.Module-ish no-ops the reference calls -------------------------------------------------
+    def to(self, *args, **kwargs):
+        return self
+
+    def eval(self):
+        return self
+
+    def float(self):
+        return self
+
+    @property
+    def logit_scale_exp(self) -> float:
+        return self.engine.logit_scale_exp
+
+    # ---- HF surface ---------------------------------------------------------------------------
+    def get_image_features(self, pixel_values: torch.Tensor = None, **_ignored) -> torch.Tensor:
+        """TF:829-863 — vision tower + visual_projection, un-normalised ``[n,512]`` float32."""
+        if pixel_values is None:
+            raise ValueError("You have to specify pixel_values")
+        return self.engine.encode_images(pixel_values)
+
+    def get_text_features(self, input_ids: torch.Tensor = None, attention_mask: Optional[torch.Tensor] = None,
+                          **_ignored) -> torch.Tensor:
+        """TF:793-825 — text tower + text_projection, un-normalised ``[n,512]`` float32."""
+        if input_ids is None:
+            raise ValueError("You have to specify input_ids")  # TF:540-541
+        return self.engine.encode_text(input_ids, attention_mask)
+
+    def forward(self, input_ids: torch.Tensor = None, pixel_values: torch.Tensor = None,
+                attention_mask: Optional[torch.Tensor] = None, return_loss: Optional[bool] = None,
+                **_ignored) -> CLIPOutput:
+        """TF:867-944 — both towers, L2-normalise, ``exp(logit_scale) * I . T^T``."""
+        if input_ids is None:
+            raise ValueError("You have to specify input_ids")
+        if pixel_values is None:
+            raise ValueError("You have to specify pixel_values")
+        img = self.engine.encode_images(pixel_values, normalize=True)
+        txt = self.engine.encode_text(input_ids, attention_mask, normalize=True)
+        lpi = self.engine.similarity(img, txt, normalize_image=False, normalize_text=False)
+        loss = None
+        if return_loss:  # clip_loss (TF:68-76): symmetric cross entropy; tiny, done with torch on the logits
+            lpt = lpi.t()
+            tgt = torch.arange(lpt.shape[0], device=lpt.device)
+            loss = (torch.nn.functional.cross_entropy(lpt, tgt) + torch.nn.functional.cross_entropy(lpt.t(), tgt)) / 2
+        return CLIPOutput(logits_per_image=lpi, logits_per_text=lpi.t(), text_embeds=txt, image_embeds=img, loss=loss)
+
+    __call__ = forward
+
+    # ---- OpenAI-clip surface (reproducibility/embedders/plip.py:48,66) ---------------------------------
+    def encode_image(self, images: torch.Tensor) -> torch.Tensor:
+        return self.engine.encode_images(images)
+
+    def encode_text(self, idx: torch.Tensor) -> torch.Tensor:
+        return self.engine.encode_text(idx)

@@ -1,0 +1,62 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/plip_b200.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from plip_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "plip_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"PLIP_API\s+[\w\s\*]+?\b(plip_\w+)\s*\(", hdr)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    names = _declared()
+    assert len(names) >= 20
+    L = _lib.lib(strict=True)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in plip_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_abi_version_and_layout_queries():
+    L = _lib.lib()
+    assert L.plip_abi_version() == 1
+    n = L.plip_weights_num_tensors()
+    assert n == 5 + 12 * 12 + 3 + 2 + 12 * 12 + 3
+    prev_end = 0
+    total_bf16 = 0
+    for i in range(n):
+        ti = _lib.TensorInfo()
+        assert L.plip_weights_tensor_info(i, C.byref(ti)) == 0
+        assert ti.offset % 256 == 0 and ti.offset >= prev_end
+        assert ti.numel == ti.rows * ti.cols
+        prev_end = ti.offset + ti.numel * (2 if ti.dtype == 1 else 4)
+        total_bf16 += ti.numel if ti.dtype == 1 else 0
+    assert prev_end <= L.plip_weights_blob_bytes() < prev_end + 256
+    # all GEMM weights: vision 12*(4*768^2 + 2*768*3072) + patch + proj; text 12*(4*512^2+2*512*2048) + proj
+    assert total_bf16 == 12 * (4 * 768 * 768 + 2 * 768 * 3072) + 768 * 3072 + 512 * 768 + \
+        12 * (4 * 512 * 512 + 2 * 512 * 2048) + 512 * 512
+    assert L.plip_workspace_bytes(1024) > 700e6
+    assert L.plip_workspace_bytes(0) == 0
+
+
+def test_errors_are_codes_not_exceptions():
+    L = _lib.lib()
+    ti = _lib.TensorInfo()
+    assert L.plip_weights_tensor_info(10 ** 6, C.byref(ti)) != 0
+    assert "out of range" in _lib.last_error()
+    h = C.c_void_p()
+    buf = (C.c_char * 16)()
+    rc = L.plip_create(C.cast(buf, C.c_void_p), 16, C.c_float(1.0), 0, 8, C.byref(h))
+    assert rc != 0 and "blob" in _lib.last_error()
+    with pytest.raises(RuntimeError, match="blob"):
+        _lib.check(rc, "plip_create")
+    assert L.plip_destroy(None) == 0
