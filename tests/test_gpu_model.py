@@ -1,0 +1,186 @@
+"""Whole-path parity on the GPU: CUDA engine vs the oracle and the committed golden vectors.
+
+Tolerances (stated by BASELINE.json's north_star / SURVEY.md §7): per-vector embedding cosine >= 1 - 1e-4
+vs the fp32 reference; |dlogits| <= 1e-3 for the similarity head on identical embeddings; end-to-end
+logits (bf16 GEMM operands upstream) are reported against a looser, explicitly stated bound."""
+import numpy as np
+import PIL.Image
+import pytest
+import torch
+
+from oracle import clip_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+COS_TOL = 1e-4
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_vision_hidden_states_layerwise(engine, state_dict):
+    px = synth.pixel_values(4)
+    hid = []
+    O.vision_transformer(state_dict, px, hidden=hid)
+    for nl in (0, 1, 6, 12):
+        h = engine.hidden_states("vision", px.cuda(), nl).cpu()
+        d = (h - hid[nl]).abs()
+        assert d.max().item() < 0.05 and d.mean().item() < 6e-3, (nl, d.max().item(), d.mean().item())
+
+
+def test_text_hidden_states_layerwise(engine, state_dict):
+    ids, mask = synth.token_ids(4)
+    hid = []
+    O.text_transformer(state_dict, ids, mask, hidden=hid)
+    h0 = engine.hidden_states("text", ids.cuda(), 0, attention_mask=mask.cuda()).cpu()
+    assert torch.equal(h0, hid[0])                     # embedding gather + add is exact fp32
+    for nl in (1, 12):
+        h = engine.hidden_states("text", ids.cuda(), nl, attention_mask=mask.cuda()).cpu()
+        d = (h - hid[nl]).abs()
+        assert d.max().item() < 0.08 and d.mean().item() < 8e-3, (nl, d.max().item(), d.mean().item())
+
+
+def test_image_embeddings_vs_golden_and_oracle(engine, state_dict, golden):
+    px = synth.pixel_values(8)
+    out = engine.encode_images(px.cuda()).cpu()
+    assert out.shape == (8, 512) and out.dtype == torch.float32
+    assert (1 - O.cosine(out, _t(golden["image_features"]))).max().item() < COS_TOL
+    assert (1 - O.cosine(out, O.get_image_features(state_dict, px))).max().item() < COS_TOL
+    outb = engine.encode_images(px.cuda().to(torch.bfloat16)).cpu()
+    assert (1 - O.cosine(outb, _t(golden["image_features"]))).max().item() < COS_TOL
+    outn = engine.encode_images(px.cuda(), normalize=True).cpu()
+    assert (outn - _t(golden["image_embeds"])).abs().max().item() < 2e-3
+    assert (outn.norm(dim=-1) - 1).abs().max().item() < 1e-5
+
+
+def test_text_embeddings_vs_golden(engine, golden):
+    ids, mask = synth.token_ids(8)
+    out = engine.encode_text(ids.cuda(), mask.cuda()).cpu()
+    assert (1 - O.cosine(out, _t(golden["text_features"]))).max().item() < COS_TOL
+    out32 = engine.encode_text(ids.to(torch.int32).cuda()).cpu()          # int32 ids, no mask
+    assert torch.equal(out32, out)                                       # eos padding + causality: mask is a no-op
+    idf, mf = synth.token_ids(4, seed=77, full_length=True)
+    outf = engine.encode_text(idf.cuda(), mf.cuda()).cpu()
+    assert (1 - O.cosine(outf, _t(golden["text_features_full77"]))).max().item() < COS_TOL
+
+
+def test_text_real_padding_mask_and_short_sequences(engine, state_dict):
+    """Masks that actually change the result (zeros before the eos) and seq_len < 77."""
+    ids, mask = synth.token_ids(6, seed=5, min_len=20)
+    mask2 = mask.clone()
+    mask2[:, 3:6] = 0
+    ref = O.get_text_features(state_dict, ids, mask2)
+    out = engine.encode_text(ids.cuda(), mask2.cuda()).cpu()
+    assert (1 - O.cosine(out, ref)).max().item() < COS_TOL
+    short = ids[:, :24].clone()
+    short[:, 23] = 49407
+    ref_s = O.get_text_features(state_dict, short, None)
+    out_s = engine.encode_text(short.cuda()).cpu()
+    assert (1 - O.cosine(out_s, ref_s)).max().item() < COS_TOL
+
+
+def test_uint8_tiles_and_reference_plip_cfg1(engine, golden):
+    """cfg1 through the device u8 path: matches the reference PLIP.encode_images golden."""
+    tiles = torch.from_numpy(synth.tiles_u8(32, seed=0))
+    out = engine.encode_images(tiles.cuda()).cpu()
+    assert (1 - O.cosine(out, _t(golden["ref_plip_encode_images_bs8"]))).max().item() < COS_TOL
+
+
+def test_similarity_head_and_clip_forward(state_dict, golden):
+    from plip_b200.modeling import PlipCLIPModel
+    model = PlipCLIPModel(state_dict, max_micro_batch=16)
+    eng = model.engine
+    # (b) similarity head alone on identical (golden) embeddings: fp32 FMA -> far inside 1e-3
+    lg = eng.similarity(_t(golden["image_embeds"]).cuda(), _t(golden["text_embeds"]).cuda()).cpu()
+    assert (lg - _t(golden["logits_per_image"])).abs().max().item() < 1e-4
+    # (c) end to end: bounded by the bf16-operand towers (~1e-2 at exp(logit_scale)=14.3)
+    px = synth.pixel_values(8)
+    ids, mask = synth.token_ids(8)
+    out = model(input_ids=ids.cuda(), pixel_values=px.cuda(), attention_mask=mask.cuda())
+    assert out.logits_per_image.shape == (8, 8)
+    assert (out.logits_per_image.cpu() - _t(golden["logits_per_image"])).abs().max().item() < 3e-2
+    assert torch.equal(out.logits_per_text, out.logits_per_image.t())
+    assert (1 - O.cosine(out.image_embeds.cpu(), _t(golden["image_embeds"]))).max().item() < COS_TOL
+    assert (1 - O.cosine(out.text_embeds.cpu(), _t(golden["text_embeds"]))).max().item() < COS_TOL
+    f = model.get_image_features(pixel_values=px.cuda())
+    assert torch.is_tensor(f) and f.shape == (8, 512)            # v4-style return: the tensor itself
+    assert torch.equal(model.encode_image(px.cuda()), f)
+    with pytest.raises(ValueError, match="doesn't match model"):
+        model.get_image_features(pixel_values=torch.zeros(1, 3, 256, 256))
+    with pytest.raises(ValueError, match="Sequence length"):
+        model.get_text_features(input_ids=torch.zeros(1, 78, dtype=torch.long))
+    with pytest.raises(ValueError, match="specify input_ids"):
+        model(pixel_values=px.cuda())
+
+
+def test_microbatching_host_path_and_determinism(engine):
+    """Size-independent properties: an image's embedding does not depend on its batch neighbours or on the
+    micro-batch split; host path == device path; run-to-run bitwise reproducible."""
+    tiles = torch.from_numpy(synth.tiles_u8(150, seed=3))          # max_micro_batch = 64 -> 3 passes, ragged tail
+    full = engine.encode_images(tiles.cuda()).cpu()
+    again = engine.encode_images(tiles.cuda()).cpu()
+    assert torch.equal(full, again)
+    part = engine.encode_images(tiles[37:38].cuda()).cpu()
+    assert (1 - O.cosine(part, full[37:38])).max().item() < 1e-6    # tile position inside a UMMA tile changes
+    assert torch.equal(engine.encode_images_host(tiles.numpy()), full)
+    assert torch.equal(engine.encode_images_host(tiles.pin_memory()), full)
+    ids, mask = synth.token_ids(100, seed=9)
+    t_full = engine.encode_text(ids.cuda(), mask.cuda()).cpu()
+    assert torch.equal(engine.encode_text_host(ids, mask), t_full)
+    assert engine.encode_images(torch.zeros(0, 3, 224, 224)).shape == (0, 512)
+
+
+def test_plip_class_drop_in(state_dict, golden):
+    """The reference-facing class: same call, same return type/shape/order as plip.PLIP (plip.py:31-53)."""
+    from plip_b200.plip import PLIP
+    p = PLIP.from_state_dict(state_dict, max_micro_batch=16)
+    tiles = synth.tiles_u8(32, seed=0)
+    pil = [PIL.Image.fromarray(t) for t in tiles]
+    for bs in (8, 32):
+        emb = p.encode_images(pil, batch_size=bs)
+        assert isinstance(emb, np.ndarray) and emb.shape == (32, 512) and emb.dtype == np.float32
+        assert (1 - O.cosine(_t(emb), _t(golden["ref_plip_encode_images_bs8"]))).max().item() < COS_TOL
+    ids, mask = synth.token_ids(8)
+    temb = p.encode_token_ids(ids, mask)
+    assert (1 - O.cosine(_t(temb), _t(golden["text_features"]))).max().item() < COS_TOL
+    sim = p._cosine_similarity(golden["heads_key"], golden["heads_space"])
+    assert np.abs(sim - golden["ref_cosine_similarity"]).max() < 1e-5
+    nn = p._nearest_neighbours(5, golden["heads_key"], golden["heads_space"])
+    assert np.array_equal(nn, golden["ref_nearest_neighbours_k5"])
+    with pytest.raises(ValueError):
+        p.encode_images([], batch_size=8)
+    with pytest.raises(AttributeError):
+        p.retrieval(["x"])
+
+
+def test_embedder_drop_in(state_dict, golden):
+    from plip_b200.embedders import CLIPEmbedder
+    from plip_b200.modeling import PlipCLIPModel
+    emb = CLIPEmbedder(PlipCLIPModel(state_dict, max_micro_batch=16), None, "plip", "mem")
+    tiles = synth.tiles_u8(32, seed=0)
+    out = emb.image_embedder([PIL.Image.fromarray(t) for t in tiles], batch_size=8)
+    ref = _t(golden["ref_plip_encode_images_bs8"])
+    ref = ref / ref.norm(dim=1, keepdim=True)                          # embedders/plip.py:53
+    assert out.shape == (32, 512) and np.abs(np.linalg.norm(out, axis=1) - 1).max() < 1e-5
+    assert (1 - O.cosine(_t(out), ref)).max().item() < COS_TOL
+    ids, _ = synth.token_ids(8)
+    tout = emb.text_embedder(list(ids.numpy()), batch_size=4)
+    tref = _t(golden["text_embeds"])
+    assert (1 - O.cosine(_t(tout), tref)).max().item() < COS_TOL
+
+
+def test_full_size_properties(state_dict):
+    """BASELINE cfg2 size (batch 1024 bf16): finite, deterministic, consistent with a small-batch run."""
+    from plip_b200.engine import Engine
+    eng = Engine(state_dict, max_micro_batch=1024)
+    px = synth.pixel_values(16).to(torch.bfloat16)
+    big = px.repeat(64, 1, 1, 1).cuda()                                  # 1024 images, 16 distinct
+    out = eng.encode_images(big)
+    assert torch.isfinite(out).all()
+    assert torch.equal(out, eng.encode_images(big))
+    small = eng.encode_images(px.cuda())
+    rep = out.view(64, 16, 512)
+    assert (1 - O.cosine(rep[63].cpu(), small.cpu())).max().item() < 1e-6
+    assert (rep - rep[0:1]).abs().max().item() < 2e-2                    # copies agree across tile positions
+    eng.close()
