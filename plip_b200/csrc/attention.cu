@@ -9,13 +9,16 @@
 // Sequences are short, so G = floor(128 / S) consecutive sequences of one head are packed into one
 // 128-row UMMA tile (vision: 2 images = 100 rows; text: 1 caption = 77 rows) and attention between
 // different sequences is masked out (block-diagonal), which keeps the arithmetic exact:
-//   TMA      Q,K,V head slices [128 rows x 64] of the QKV activation -> smem (128B swizzle), 2-stage ring
+//   TMA      Q,K,V head slices [128 rows x 64] of the QKV activation -> smem (128B swizzle)
 //   MMA 1    S[128x128] (TMEM, fp32) = Q (smem, K-major) x K^T (smem, K-major)         4 x UMMA 128x128x16
 //   softmax  thread == query row: tcgen05.ld S, mask, max, exp2, row sum; P (bf16) -> TMEM via tcgen05.st
 //   MMA 2    O[128x64] (TMEM, fp32) = P (TMEM, A operand) x V (smem, MN-major)          8 x UMMA 128x64x16
 //   epilogue tcgen05.ld O, multiply by 1/rowsum, bf16 -> global (head slice of the [rows, D] output)
 // 5 warps: warps 0-3 = softmax/epilogue (one TMEM lane quarter each), warp 4 = TMA + MMA issuer.
-// TMEM: S 128 cols + P 64 cols + O 64 cols = 256 -> two CTAs co-reside per SM and overlap each other.
+// TMEM: 128 columns per CTA — P (bf16 pairs, 64 cols) is written in place over the S columns a thread
+// has already consumed, O (64 cols) reuses the upper half of S.  With single Q/K and V smem buffers
+// (48 KB; the next tile's Q,K are fetched as soon as MMA 1 retires, its V as soon as MMA 2 retires)
+// four CTAs co-reside per SM and hide each other's serial load -> MMA -> softmax -> MMA -> store chain.
 #include "kernels.cuh"
 
 namespace plip {
@@ -25,9 +28,10 @@ namespace {
 constexpr int kAttThreads = 160;
 constexpr uint32_t kTileBytes = 128 * 64 * 2;  // one [128 x 64] bf16 operand tile
 constexpr uint32_t kStageBytes = 3 * kTileBytes;
-constexpr uint32_t kAttSmem = 2 * kStageBytes + 1024 + 256;
-constexpr uint32_t kTmemCols = 256;
-constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
+constexpr uint32_t kAttSmem = kStageBytes + 1024 + 256;
+constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kColS = 0, kColP = 0, kColO = 64;
+constexpr int kAttCtasPerSm = 4;
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
@@ -51,15 +55,15 @@ struct AttParams {
   __nv_bfloat16* out;       // [total_rows, heads*64]
 };
 
-__global__ void __launch_bounds__(kAttThreads, 2)
+__global__ void __launch_bounds__(kAttThreads, kAttCtasPerSm)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + 2 * kStageBytes;
-  auto bar_load = [&](int s) { return bar_base + 8u * s; };
-  const uint32_t bar_s = bar_base + 16, bar_p = bar_base + 24, bar_o = bar_base + 32;
-  const uint32_t tmem_slot = bar_base + 40;
+  const uint32_t bar_base = smem_base + kStageBytes;
+  const uint32_t bar_qk = bar_base, bar_v = bar_base + 8;
+  const uint32_t bar_s = bar_base + 16, bar_p = bar_base + 24, bar_o = bar_base + 32, bar_e = bar_base + 40;
+  const uint32_t tmem_slot = bar_base + 48;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -67,11 +71,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
-    mbar_init(bar_load(0), 1);
-    mbar_init(bar_load(1), 1);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 128);
     mbar_init(bar_o, 1);
+    mbar_init(bar_e, 128);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<1>(tmem_slot, kTmemCols);
@@ -88,36 +93,45 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S = Q K^T, both K-major
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // O = P V, V is MN-major
-      auto issue_load = [&](int64_t tile, int stage) {
+      const uint32_t sq = smem_base, sk = smem_base + kTileBytes, sv = smem_base + 2 * kTileBytes;
+      auto coords = [&](int64_t tile, int& h, int32_t& row0) {
         const int64_t st = tile / p.heads;
-        const int h = (int)(tile - st * p.heads);
-        const int32_t row0 = (int32_t)(st * p.rows_per_tile);
-        const uint32_t dst = smem_base + stage * kStageBytes;
-        mbar_arrive_expect_tx(bar_load(stage), kStageBytes);
-        tma_load_2d(dst, &tmQKV, bar_load(stage), h * kHeadDim, row0);
-        tma_load_2d(dst + kTileBytes, &tmQKV, bar_load(stage), D + h * kHeadDim, row0);
-        tma_load_2d(dst + 2 * kTileBytes, &tmQKV, bar_load(stage), 2 * D + h * kHeadDim, row0);
+        h = (int)(tile - st * p.heads);
+        row0 = (int32_t)(st * p.rows_per_tile);
+      };
+      auto issue_qk = [&](int64_t tile) {
+        int h; int32_t row0;
+        coords(tile, h, row0);
+        mbar_arrive_expect_tx(bar_qk, 2 * kTileBytes);
+        tma_load_2d(sq, &tmQKV, bar_qk, h * kHeadDim, row0);
+        tma_load_2d(sk, &tmQKV, bar_qk, D + h * kHeadDim, row0);
+      };
+      auto issue_v = [&](int64_t tile) {
+        int h; int32_t row0;
+        coords(tile, h, row0);
+        mbar_arrive_expect_tx(bar_v, kTileBytes);
+        tma_load_2d(sv, &tmQKV, bar_v, 2 * D + h * kHeadDim, row0);
       };
       int64_t tile = blockIdx.x;
-      if (tile < num_tiles) issue_load(tile, 0);
+      if (tile < num_tiles) { issue_qk(tile); issue_v(tile); }
       uint32_t it = 0;
+      const uint64_t qdesc = make_smem_desc_sw128(sq, 1024, 16);
+      const uint64_t kdesc = make_smem_desc_sw128(sk, 1024, 16);
       for (; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int stage = it & 1;
+        const uint32_t par = it & 1u;
         const int64_t next = tile + gridDim.x;
-        if (next < num_tiles) issue_load(next, stage ^ 1);  // previous user of that stage finished (bar_o)
-        mbar_wait(bar_load(stage), (it >> 1) & 1u);
+        mbar_wait(bar_qk, par);
+        if (it > 0) mbar_wait(bar_e, par ^ 1u);  // previous tile's O (aliases S) has been read out
         tc_fence_after();
-        const uint32_t sq = smem_base + stage * kStageBytes;
-        const uint64_t qdesc = make_smem_desc_sw128(sq, 1024, 16);
-        const uint64_t kdesc = make_smem_desc_sw128(sq + kTileBytes, 1024, 16);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss<1>(tmem_base + kColS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit<1>(bar_s);
-        // wait for the softmax warps to publish P in TMEM
-        mbar_wait(bar_p, it & 1u);
+        mbar_wait(bar_s, par);                   // MMA 1 retired: Q/K buffers are free
+        if (next < num_tiles) issue_qk(next);
+        mbar_wait(bar_p, par);                   // softmax warps published P in TMEM
+        mbar_wait(bar_v, par);
         tc_fence_after();
-        const uint32_t sv = sq + 2 * kTileBytes;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // V tile [128 keys][64 dh]: advancing 16 keys (one UMMA K) = 16 rows of 128 B
@@ -125,7 +139,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
           umma_ts(tmem_base + kColO, tmem_base + kColP + k * 8, vdesc, idesc_o, k != 0 ? 1u : 0u);
         }
         umma_commit<1>(bar_o);
-        mbar_wait(bar_o, it & 1u);  // smem stage and S/P columns are free again
+        mbar_wait(bar_o, par);                   // MMA 2 retired: V buffer is free
+        if (next < num_tiles) issue_v(next);
       }
     }
   } else {
@@ -223,6 +238,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
         uint32_t v[32];
         tmem_ld32(lane_base + kColO + 32 * j, v);
         tmem_ld_wait();
+        if (j == 1) {  // O fully read: the next tile's S = Q K^T may overwrite these columns
+          tc_fence_before();
+          mbar_arrive(bar_e);
+        }
         if (store) {
           uint4* o4 = reinterpret_cast<uint4*>(p.out + grow * D + h * kHeadDim + 32 * j);
 #pragma unroll
@@ -236,7 +255,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
           }
         }
       }
-      tc_fence_before();  // order our TMEM reads before the next tile's MMAs (via bar_p of that tile)
     }
   }
 
@@ -260,7 +278,7 @@ int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int h
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    grid_cap = 2 * sms;
+    grid_cap = kAttCtasPerSm * sms;
     configured = true;
   }
   const int D = heads * kHeadDim;
