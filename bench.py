@@ -81,6 +81,25 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def usable_cores() -> int:
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota (a container
+    that sees 128 logical CPUs but is limited to a few would thrash with 128 threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per) + 0.5)))
+    except Exception:  # noqa: BLE001
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, min(n, int(os.environ.get("PLIP_BENCH_MAX_THREADS", "64"))))
+
+
 def _dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -94,7 +113,7 @@ def run_reference(args):
         return 0
     from oracle import clip_oracle as O, synth, weights
     torch.set_grad_enabled(False)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     sd = weights.make_state_dict(0)
     bs = 32                                           # batch 32 on the host cores
@@ -130,7 +149,7 @@ def run_reference(args):
 # =================================================================================================
 def cpu_baseline_sample():
     from oracle import clip_oracle as O, synth, weights
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     sd = weights.make_state_dict(0)
     bs = 32

@@ -87,6 +87,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
       *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
 
   const int64_t num_tiles = p.seq_tiles * p.heads;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 4) {
     // ===================== TMA producer + MMA issuer =====================
@@ -297,8 +299,7 @@ int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int h
   p.out = out;
   const int64_t tiles = p.seq_tiles * heads;
   const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
-  attention_kernel<<<grid, kAttThreads, kAttSmem, st>>>(tm, p);
-  PLIP_CUDA_CHECK(cudaGetLastError());
+  PLIP_CUDA_CHECK(launch_pdl(attention_kernel, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tm, p));
   ++g_launch_count;
   return 0;
 }

@@ -28,6 +28,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 template <int FMT>
 __global__ void __launch_bounds__(kEwThreads) im2col_kernel(const void* __restrict__ pixels,
                                                             __nv_bfloat16* __restrict__ out, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int kX8 = kImage / 8;  // 28 groups of 8 pixels per image row
   const int64_t total = (FMT == PLIP_PIX_U8_NHWC) ? n * kImage * kX8 : n * 3 * kImage * kX8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -90,6 +92,8 @@ __global__ void __launch_bounds__(kEwThreads) layernorm_kernel(const float* __re
                                                                const float* __restrict__ beta,
                                                                float* __restrict__ out_f32,
                                                                __nv_bfloat16* __restrict__ out_bf16) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int V = D / 128;  // float4 per lane
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -143,6 +147,8 @@ __global__ void __launch_bounds__(kEwThreads) text_embed_kernel(const IdT* __res
                                                                 const float* __restrict__ tok,
                                                                 const float* __restrict__ pos,
                                                                 float* __restrict__ x) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -168,6 +174,8 @@ template <typename IdT>
 __global__ void __launch_bounds__(kEwThreads) eos_row_kernel(const IdT* __restrict__ ids, int64_t n,
                                                              int seq_len, int eos_id,
                                                              int32_t* __restrict__ row_index) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -187,6 +195,8 @@ __global__ void __launch_bounds__(kEwThreads) eos_row_kernel(const IdT* __restri
 template <typename IdT>
 __global__ void __launch_bounds__(kEwThreads) mask_to_i32_kernel(const IdT* __restrict__ m, int64_t count,
                                                                  int32_t* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
        i += (int64_t)gridDim.x * blockDim.x)
     out[i] = m[i] != 0 ? 1 : 0;
@@ -196,6 +206,8 @@ __global__ void __launch_bounds__(kEwThreads) mask_to_i32_kernel(const IdT* __re
 __global__ void __launch_bounds__(kEwThreads) cls_rows_kernel(const float* __restrict__ cls,
                                                               const float* __restrict__ pos, int64_t n,
                                                               float* __restrict__ x) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int V = kVisDim / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * V;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -211,6 +223,8 @@ __global__ void __launch_bounds__(kEwThreads) cls_rows_kernel(const float* __res
 // x[r] /= sqrt(sum x[r]^2): _get_vector_norm, no epsilon (TF:57-65,923-924). One warp per row.
 __global__ void __launch_bounds__(kEwThreads) l2_normalize_kernel(float* __restrict__ x, int64_t rows,
                                                                   int dim) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -239,9 +253,9 @@ int launch_im2col(const void* pixels, int fmt, int64_t n, __nv_bfloat16* out, cu
   const int64_t items = (fmt == PLIP_PIX_U8_NHWC ? 1 : 3) * n * kImage * (kImage / 8);
   const int grid = grid_for(items, kEwThreads);
   switch (fmt) {
-    case PLIP_PIX_F32_NCHW: im2col_kernel<PLIP_PIX_F32_NCHW><<<grid, kEwThreads, 0, st>>>(pixels, out, n); break;
-    case PLIP_PIX_BF16_NCHW: im2col_kernel<PLIP_PIX_BF16_NCHW><<<grid, kEwThreads, 0, st>>>(pixels, out, n); break;
-    case PLIP_PIX_U8_NHWC: im2col_kernel<PLIP_PIX_U8_NHWC><<<grid, kEwThreads, 0, st>>>(pixels, out, n); break;
+    case PLIP_PIX_F32_NCHW: PLIP_CUDA_CHECK(launch_pdl(im2col_kernel<PLIP_PIX_F32_NCHW>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
+    case PLIP_PIX_BF16_NCHW: PLIP_CUDA_CHECK(launch_pdl(im2col_kernel<PLIP_PIX_BF16_NCHW>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
+    case PLIP_PIX_U8_NHWC: PLIP_CUDA_CHECK(launch_pdl(im2col_kernel<PLIP_PIX_U8_NHWC>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
     default: set_last_error("im2col: unknown pixel format %d", fmt); return -2;
   }
   PLIP_CUDA_CHECK(cudaGetLastError());
@@ -256,9 +270,9 @@ int launch_layernorm(const float* x, const int32_t* row_index, int64_t in_row_st
   PLIP_REQUIRE(in_row_stride % 4 == 0, "layernorm: row stride must be a multiple of 4 floats");
   const int grid = grid_for(rows, kEwThreads / 32);
   if (dim == kVisDim)
-    layernorm_kernel<kVisDim><<<grid, kEwThreads, 0, st>>>(x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16);
+    PLIP_CUDA_CHECK(launch_pdl(layernorm_kernel<kVisDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16));
   else if (dim == kTxtDim)
-    layernorm_kernel<kTxtDim><<<grid, kEwThreads, 0, st>>>(x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16);
+    PLIP_CUDA_CHECK(launch_pdl(layernorm_kernel<kTxtDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16));
   else {
     set_last_error("layernorm: unsupported dim %d (768 or 512)", dim);
     return -2;
@@ -275,11 +289,11 @@ int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, co
   const int grid = grid_for(n * seq_len, kEwThreads / 32);
   const int grid2 = grid_for(n, kEwThreads / 32);
   if (ids_dtype == PLIP_IDS_I64) {
-    text_embed_kernel<long long><<<grid, kEwThreads, 0, st>>>(static_cast<const long long*>(ids), n, seq_len, tok, pos, x);
-    eos_row_kernel<long long><<<grid2, kEwThreads, 0, st>>>(static_cast<const long long*>(ids), n, seq_len, eos_id, eos_rows);
+    PLIP_CUDA_CHECK(launch_pdl(text_embed_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, tok, pos, x));
+    PLIP_CUDA_CHECK(launch_pdl(eos_row_kernel<long long>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, eos_id, eos_rows));
   } else if (ids_dtype == PLIP_IDS_I32) {
-    text_embed_kernel<int><<<grid, kEwThreads, 0, st>>>(static_cast<const int*>(ids), n, seq_len, tok, pos, x);
-    eos_row_kernel<int><<<grid2, kEwThreads, 0, st>>>(static_cast<const int*>(ids), n, seq_len, eos_id, eos_rows);
+    PLIP_CUDA_CHECK(launch_pdl(text_embed_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, tok, pos, x));
+    PLIP_CUDA_CHECK(launch_pdl(eos_row_kernel<int>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, eos_id, eos_rows));
   } else {
     set_last_error("text_embed: unknown ids dtype %d", ids_dtype);
     return -2;
@@ -292,16 +306,16 @@ int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, co
 int launch_mask_to_i32(const void* mask, int dtype, int64_t count, int32_t* out, cudaStream_t st) {
   const int grid = grid_for(count, kEwThreads);
   if (dtype == PLIP_IDS_I64)
-    mask_to_i32_kernel<long long><<<grid, kEwThreads, 0, st>>>(static_cast<const long long*>(mask), count, out);
+    PLIP_CUDA_CHECK(launch_pdl(mask_to_i32_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(mask), count, out));
   else
-    mask_to_i32_kernel<int><<<grid, kEwThreads, 0, st>>>(static_cast<const int*>(mask), count, out);
+    PLIP_CUDA_CHECK(launch_pdl(mask_to_i32_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(mask), count, out));
   PLIP_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return 0;
 }
 
 int launch_cls_rows(const float* cls, const float* pos, int64_t n, float* x, cudaStream_t st) {
-  cls_rows_kernel<<<grid_for(n * (kVisDim / 4), kEwThreads), kEwThreads, 0, st>>>(cls, pos, n, x);
+  PLIP_CUDA_CHECK(launch_pdl(cls_rows_kernel, dim3(grid_for(n * (kVisDim / 4), kEwThreads)), dim3(kEwThreads), 0, st, 1, cls, pos, n, x));
   PLIP_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return 0;
@@ -309,7 +323,7 @@ int launch_cls_rows(const float* cls, const float* pos, int64_t n, float* x, cud
 
 int launch_l2_normalize(float* x, int64_t rows, int dim, cudaStream_t st) {
   PLIP_REQUIRE(rows > 0 && dim > 0, "l2_normalize: bad shape");
-  l2_normalize_kernel<<<grid_for(rows, kEwThreads / 32), kEwThreads, 0, st>>>(x, rows, dim);
+  PLIP_CUDA_CHECK(launch_pdl(l2_normalize_kernel, dim3(grid_for(rows, kEwThreads / 32)), dim3(kEwThreads), 0, st, 1, x, rows, dim));
   PLIP_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return 0;

@@ -230,6 +230,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base =
       *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
+  pdl_wait();               // the producer of A / the residual stream has completed
+  pdl_launch_dependents();  // let the next kernel's prologue fill SMs as they free up
 
   const int num_n_blk = p.N / BN;
   const int num_m_blk = (p.M + BM * CG - 1) / (BM * CG);
@@ -404,19 +406,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   int groups = max_groups;
   if (groups > num_tiles) groups = num_tiles;
 
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(groups * CG);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  PLIP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  PLIP_CUDA_CHECK(launch_pdl(kern, dim3(groups * CG), dim3(kThreads), C::SMEM_BYTES, stream, CG, tmA, tmB, p));
   ++g_launch_count;
   return 0;
 }
@@ -438,7 +428,7 @@ int launch_epi(const GemmArgs& g, cudaStream_t stream) {
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   PLIP_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "launch_gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   PLIP_REQUIRE(g.K % BK == 0, "launch_gemm: K=%d must be a multiple of %d", g.K, BK);
-  PLIP_REQUIRE(g.N % 128 == 0, "launch_gemm: N=%d must be a multiple of 128", g.N);
+  PLIP_REQUIRE(g.N % 128 == 0 || (g.N % 192 == 0 && g.force_bn == 192), "launch_gemm: N=%d must be a multiple of 128", g.N);
   PLIP_REQUIRE((g.lda % 8) == 0 && (g.ldw % 8) == 0 && (g.ldo % 8) == 0,
                "launch_gemm: leading dimensions must be multiples of 8 elements");
   PLIP_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.W) & 15) == 0 &&
@@ -449,8 +439,10 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   int cg = g.force_cg ? g.force_cg : (env_cg ? env_cg : 2);
   int bn = g.force_bn ? g.force_bn : (env_bn ? env_bn : 256);
   if (g.N % bn != 0) bn = 128;
-  PLIP_REQUIRE((cg == 1 || cg == 2) && (bn == 128 || bn == 256), "launch_gemm: bad config cg=%d bn=%d", cg, bn);
+  PLIP_REQUIRE((cg == 1 || cg == 2) && (bn == 128 || bn == 256 || (bn == 192 && cg == 2)),
+               "launch_gemm: bad config cg=%d bn=%d", cg, bn);
   if (cg == 1) return bn == 256 ? launch_epi<1, 256>(g, stream) : launch_epi<1, 128>(g, stream);
+  if (bn == 192) return launch_epi<2, 192>(g, stream);
   return bn == 256 ? launch_epi<2, 256>(g, stream) : launch_epi<2, 128>(g, stream);
 }
 

@@ -23,6 +23,8 @@ similarity_kernel(const float* __restrict__ A, int64_t n, const float* __restric
   __shared__ float Bs[TK][TN + 4];
   __shared__ float inv_a[TM], inv_b[TN];
 
+  pdl_wait();
+  pdl_launch_dependents();
   const int t = threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.y * TM;
   const int64_t col0 = (int64_t)blockIdx.x * TN;
@@ -104,6 +106,8 @@ similarity_topk_kernel(const float* __restrict__ Q, int64_t n, const float* __re
   __shared__ float ls[4][kTopkMax];
   __shared__ int li[4][kTopkMax];
   __shared__ float red[4];
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x;
 
@@ -174,8 +178,8 @@ int launch_similarity(const float* a, int64_t n, const float* b, int64_t m, floa
   const int64_t gy = (n + TM - 1) / TM, gx = (m + TN - 1) / TN;
   PLIP_REQUIRE(gy <= 65535, "similarity: n=%lld too large for one launch (chunk rows)", (long long)n);
   dim3 grid((unsigned)gx, (unsigned)gy);
-  similarity_kernel<<<grid, kSimThreads, 0, st>>>(a, n, b, m, kProj, scale, norm_a ? 1 : 0, norm_b ? 1 : 0, out, ldo);
-  PLIP_CUDA_CHECK(cudaGetLastError());
+  PLIP_CUDA_CHECK(launch_pdl(similarity_kernel, grid, dim3(kSimThreads), 0, st, 1, a, n, b, m, (int)kProj, scale,
+                             norm_a ? 1 : 0, norm_b ? 1 : 0, out, ldo));
   ++g_launch_count;
   return 0;
 }
@@ -185,9 +189,8 @@ int launch_similarity_topk(const float* q, int64_t n, const float* s, int64_t m,
   PLIP_REQUIRE(n > 0 && m > 0, "similarity_topk: empty operand");
   PLIP_REQUIRE(k >= 1 && k <= kTopkMax, "similarity_topk: k=%d out of range [1,%d]", k, kTopkMax);
   PLIP_REQUIRE(n <= 0x7fffffff && m <= 0x7fffffff, "similarity_topk: operand too large");
-  similarity_topk_kernel<<<(unsigned)n, kTopkThreads, 0, st>>>(q, n, s, m, kProj, scale, norm_q ? 1 : 0,
-                                                             norm_s ? 1 : 0, k, idx, val);
-  PLIP_CUDA_CHECK(cudaGetLastError());
+  PLIP_CUDA_CHECK(launch_pdl(similarity_topk_kernel, dim3((unsigned)n), dim3(kTopkThreads), 0, st, 1, q, n, s, m,
+                             (int)kProj, scale, norm_q ? 1 : 0, norm_s ? 1 : 0, k, idx, val));
   ++g_launch_count;
   return 0;
 }
