@@ -173,15 +173,25 @@ def kernel_rooflines(eng, peaks, stream):
     from plip_b200._lib import check
     L = eng._L
     M = PAIRS * 50
-    shapes = [("qkv", 0, 2304, 768), ("out_proj+resid", 2, 768, 768), ("fc1+gelu", 1, 3072, 768), ("fc2+resid", 2, 768, 3072)]
+    # (name, epilogue id, N, K): exactly the four GEMM launches of one vision encoder layer
+    shapes = [("ln1+qkv", 5, 2304, 768), ("out_proj+resid", 2, 768, 768), ("ln2+fc1+gelu", 6, 3072, 768),
+              ("fc2+resid", 2, 768, 3072)]
     res = []
+    stats = torch.zeros(M, 4, 2, device="cuda")
+    stats[:, 0, 1] = 768.0                                   # mean 0, var 1 -> rstd ~ 1
     for name, epi, N, K in shapes:
         A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         W = (torch.randn(N, K, device="cuda") * 0.03).to(torch.bfloat16)
         bias = torch.zeros(N, device="cuda")
+        colsum = W.float().sum(1).contiguous()
         out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if epi == 2 else torch.bfloat16)
+        xb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if epi == 2 else None
+        st_out = torch.empty(M, 4, 2, device="cuda") if epi == 2 else None
         call = lambda: check(L.plip_dbg_gemm(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), out.data_ptr(), N,  # noqa: E731
-                                             None, epi, 0, 0, stream), "gemm")
+                                             None, epi, 0, 0, colsum.data_ptr() if epi >= 5 else None,
+                                             stats.data_ptr() if epi >= 5 else None, 1 if epi >= 5 else 0,
+                                             xb.data_ptr() if xb is not None else None,
+                                             st_out.data_ptr() if st_out is not None else None, stream), "gemm")
         for _ in range(3):
             call()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -194,7 +204,7 @@ def kernel_rooflines(eng, peaks, stream):
         tf = 2.0 * M * N * K / ms / 1e9
         res.append({"kernel": f"gemm_tcgen05[{name}]", "M": M, "N": N, "K": K, "us": ms * 1e3, "tflops": tf,
                     "frac_of_burst_peak": tf / peaks["bf16_tflops"]})
-        del A, W, out
+        del A, W, out, xb, st_out
     return res
 
 

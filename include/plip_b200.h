@@ -27,7 +27,7 @@ extern "C" {
 
 #define PLIP_API __attribute__((visibility("default")))
 
-#define PLIP_B200_ABI_VERSION 1
+#define PLIP_B200_ABI_VERSION 2
 
 /* Model constants (TF:configuration_clip.py:47-64,97-109,160-161). */
 #define PLIP_IMAGE_SIZE 224
@@ -65,9 +65,13 @@ typedef struct plip_tensor_info {
   int32_t dtype;    /* 0 = float32, 1 = bfloat16 */
   int32_t rows;     /* logical 2-D shape (rows x cols), cols == 1 for vectors */
   int32_t cols;
-  int32_t fused;    /* 0 = plain copy of the named tensor; 1 = q/k/v rows concatenated:
-                       name holds the q tensor, k and v follow ("...q_proj" -> k_proj, v_proj);
-                       the q rows (weight and bias) are pre-scaled by head_dim^-0.5 = 0.125 */
+  int32_t fused;    /* 0 = plain copy of the named tensor.
+                       bit 0 (1): q/k/v rows concatenated — name holds the q tensor, k and v follow
+                         ("...q_proj" -> k_proj, v_proj); the q rows are pre-scaled by head_dim^-0.5 = 0.125.
+                       bit 1 (2): the preceding LayerNorm (layer_norm1 for q_proj, layer_norm2 for fc1;
+                         TF:371,380) is folded in: weight' = bf16(gamma o W), bias' = bias + W beta, and the
+                         pseudo-tensor "<...>.colsum"[n] = sum_k float(weight'[n,k]); the kernels then compute
+                         rstd_r * (x_bf16 . weight'_n - mean_r * colsum_n) + bias'_n  ==  LN(x) . W_n + bias_n. */
 } plip_tensor_info_t;
 
 PLIP_API int plip_weights_num_tensors(void);
@@ -131,9 +135,14 @@ PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int i
                                    float* out_host, int normalize);
 
 /* ---- per-kernel test hooks (used by tests/ only; stream-ordered, device pointers) ------------ */
+/* epilogue: 0 bias->bf16, 1 bias+QuickGELU->bf16, 2 x_f32 += acc+bias (optionally also xb_out bf16 copy +
+ * stats_out [M,4,2] row statistics), 3 patch scatter + pos, 4 plain f32, 5/6 = 0/1 with the LayerNorm fold
+ * (colsum [N], stats_in [M,4,2] with n_partials valid slots). */
 PLIP_API int plip_dbg_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K,
                            const float* bias, void* out, int ldo, const float* pos, int epilogue, int cta_group,
-                           int block_n, void* stream);
+                           int block_n, const float* colsum, const float* stats_in, int n_partials, void* xb_out,
+                           float* stats_out, void* stream);
+PLIP_API int plip_dbg_rowstats_cast(const float* x, int64_t rows, int dim, void* xb_bf16, float* stats, void* stream);
 PLIP_API int plip_dbg_layernorm(const float* x, int64_t rows, int dim, int64_t in_row_stride,
                                 const float* gamma, const float* beta, float* out_f32, void* out_bf16,
                                 void* stream);

@@ -137,6 +137,40 @@ __global__ void __launch_bounds__(kEwThreads) layernorm_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// bf16 copy + per-row (sum, sum of squares) of the fp32 residual stream: the A operand and the
+// statistics a LayerNorm-folded GEMM needs (EPI_LN_*), for rows that were not produced by a residual
+// GEMM epilogue (start of a tower).  One warp per row; slot 0 of the statistics row is written.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kEwThreads) rowstats_cast_kernel(const float* __restrict__ x, int64_t rows,
+                                                                   __nv_bfloat16* __restrict__ xb,
+                                                                   float2* __restrict__ stats) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int V = D / 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + r * D);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float4 v = xr[lane + 32 * j];
+      s1 += (v.x + v.y) + (v.z + v.w);
+      s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      reinterpret_cast<uint2*>(xb + r * D)[lane + 32 * j] = u;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) stats[r * kStatSlots] = make_float2(s1, s2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Text embeddings: x[b*S + t] = token_embedding[ids[b,t]] + position_embedding[t]   (TF:253-256).
 // One warp per token row (512 fp32 = 4 float4 per lane).  Ids are clamped into the vocabulary for
 // memory safety (the reference would raise an IndexError on out-of-range ids).
@@ -278,6 +312,21 @@ int launch_layernorm(const float* x, const int32_t* row_index, int64_t in_row_st
     return -2;
   }
   PLIP_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_rowstats_cast(const float* x, int64_t rows, int dim, __nv_bfloat16* xb, float2* stats, cudaStream_t st) {
+  PLIP_REQUIRE(rows > 0, "rowstats_cast: rows must be positive");
+  const int grid = grid_for(rows, kEwThreads / 32);
+  if (dim == kVisDim)
+    PLIP_CUDA_CHECK(launch_pdl(rowstats_cast_kernel<kVisDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, rows, xb, stats));
+  else if (dim == kTxtDim)
+    PLIP_CUDA_CHECK(launch_pdl(rowstats_cast_kernel<kTxtDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, rows, xb, stats));
+  else {
+    set_last_error("rowstats_cast: unsupported dim %d", dim);
+    return -2;
+  }
   ++g_launch_count;
   return 0;
 }

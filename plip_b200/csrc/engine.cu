@@ -40,16 +40,17 @@ void add(std::vector<Spec>& v, const std::string& name, int dtype, int rows, int
 void add_tower(std::vector<Spec>& v, const std::string& pfx, int D, int FF) {
   for (int l = 0; l < kLayers; ++l) {
     const std::string p = pfx + ".encoder.layers." + std::to_string(l);
-    add(v, p + ".layer_norm1.weight", 0, D, 1);
-    add(v, p + ".layer_norm1.bias", 0, D, 1);
-    add(v, p + ".self_attn.q_proj.weight", 1, 3 * D, D, 1);  // q|k|v rows, q pre-scaled by 0.125
-    add(v, p + ".self_attn.q_proj.bias", 0, 3 * D, 1, 1);
+    // fused bit 0: q|k|v rows concatenated, q pre-scaled by 0.125; bit 1: LayerNorm folded in
+    // (layer_norm1 for q_proj, layer_norm2 for fc1): W' = bf16(gamma o W), bias' = bias + W beta,
+    // colsum[n] = sum_k W'[n,k].  layer_norm1/2 themselves never reach the device.
+    add(v, p + ".self_attn.q_proj.weight", 1, 3 * D, D, 3);
+    add(v, p + ".self_attn.q_proj.bias", 0, 3 * D, 1, 3);
+    add(v, p + ".self_attn.q_proj.colsum", 0, 3 * D, 1, 3);
     add(v, p + ".self_attn.out_proj.weight", 1, D, D);
     add(v, p + ".self_attn.out_proj.bias", 0, D, 1);
-    add(v, p + ".layer_norm2.weight", 0, D, 1);
-    add(v, p + ".layer_norm2.bias", 0, D, 1);
-    add(v, p + ".mlp.fc1.weight", 1, FF, D);
-    add(v, p + ".mlp.fc1.bias", 0, FF, 1);
+    add(v, p + ".mlp.fc1.weight", 1, FF, D, 2);
+    add(v, p + ".mlp.fc1.bias", 0, FF, 1, 2);
+    add(v, p + ".mlp.fc1.colsum", 0, FF, 1, 2);
     add(v, p + ".mlp.fc2.weight", 1, D, FF);
     add(v, p + ".mlp.fc2.bias", 0, D, 1);
   }
@@ -89,7 +90,7 @@ uint64_t blob_bytes() {
 }
 
 struct LayerW {
-  const float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *b1, *b2;
+  const float *bqkv, *sqkv, *bo, *b1, *s1, *b2;
   const __nv_bfloat16 *wqkv, *wo, *w1, *w2;
 };
 
@@ -120,7 +121,9 @@ struct plip_engine {
   const __nv_bfloat16* t_proj = nullptr;
   // workspace (sized for max_mb)
   float* X = nullptr;            // residual stream fp32 [rows, D]
-  __nv_bfloat16* Xn = nullptr;   // LN output / attention output [rows, D]
+  __nv_bfloat16* Xn = nullptr;   // bf16 copy of the residual stream (A operand of the LN-folded GEMMs) [rows, D]
+  __nv_bfloat16* AO = nullptr;   // attention output [rows, D]
+  float2* stats = nullptr;       // per-row (sum, sumsq) partials of X [rows, kStatSlots]
   __nv_bfloat16* QKV = nullptr;  // [rows, 3D]
   __nv_bfloat16* H = nullptr;    // fc1 output [rows, FF]; aliases the im2col matrix [mb*49, 3072]
   __nv_bfloat16* pooled = nullptr;  // [mb, 768]
@@ -153,11 +156,9 @@ int bind_weights(plip_engine* e) {
   auto nextb = [&]() { return wptr<__nv_bfloat16>(e, v[i++]); };
   auto tower = [&](LayerW* L) {
     for (int l = 0; l < kLayers; ++l) {
-      L[l].ln1_g = nextf(); L[l].ln1_b = nextf();
-      L[l].wqkv = nextb(); L[l].bqkv = nextf();
+      L[l].wqkv = nextb(); L[l].bqkv = nextf(); L[l].sqkv = nextf();
       L[l].wo = nextb(); L[l].bo = nextf();
-      L[l].ln2_g = nextf(); L[l].ln2_b = nextf();
-      L[l].w1 = nextb(); L[l].b1 = nextf();
+      L[l].w1 = nextb(); L[l].b1 = nextf(); L[l].s1 = nextf();
       L[l].w2 = nextb(); L[l].b2 = nextf();
     }
   };
@@ -178,7 +179,7 @@ int bind_weights(plip_engine* e) {
 }
 
 struct WsLayout {
-  size_t x, xn, qkv, h, pooled, rowidx, kmask, total;
+  size_t x, xn, ao, stats, qkv, h, pooled, rowidx, kmask, total;
 };
 
 WsLayout ws_layout(int mb) {
@@ -189,6 +190,8 @@ WsLayout ws_layout(int mb) {
   size_t off = 0;
   w.x = off; off += al(mx(rv * kVisDim, rt * kTxtDim) * 4);
   w.xn = off; off += al(mx(rv * kVisDim, rt * kTxtDim) * 2);
+  w.ao = off; off += al(mx(rv * kVisDim, rt * kTxtDim) * 2);
+  w.stats = off; off += al(mx(rv, rt) * kStatSlots * sizeof(float2));
   w.qkv = off; off += al(mx(rv * 3 * kVisDim, rt * 3 * kTxtDim) * 2);
   w.h = off; off += al(mx(mx(rv * kVisFF, rt * kTxtFF), (size_t)mb * kPatches * kPatchK) * 2);
   w.pooled = off; off += al((size_t)mb * kVisDim * 2);
@@ -198,32 +201,41 @@ WsLayout ws_layout(int mb) {
   return w;
 }
 
+// Encoder layers with both LayerNorms folded into the consuming GEMMs.  On entry X holds the residual
+// stream; Xn / stats are (re)derived from it here and afterwards maintained by the residual epilogues.
 int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int FF, int heads, bool causal,
                const int32_t* kmask, int num_layers, cudaStream_t st) {
   const int64_t M = n_seq * S;
   PLIP_REQUIRE(M <= 0x7fffffff / 4, "micro-batch too large");
+  if (num_layers <= 0) return 0;
+  if (int rc = launch_rowstats_cast(e->X, M, D, e->Xn, e->stats, st)) return rc;
+  int np = 1;
   for (int l = 0; l < num_layers; ++l) {
     const LayerW& w = L[l];
     // x = x + out_proj(attn(LN1(x)))                                     TF:modeling_clip.py:370-377
-    if (int rc = launch_layernorm(e->X, nullptr, D, M, D, w.ln1_g, w.ln1_b, nullptr, e->Xn, st)) return rc;
     GemmArgs g;
     g.A = e->Xn; g.lda = D; g.W = w.wqkv; g.ldw = D; g.M = (int)M; g.N = 3 * D; g.K = D;
-    g.bias = w.bqkv; g.out = e->QKV; g.ldo = 3 * D; g.epi = EPI_BIAS_BF16;
+    g.bias = w.bqkv; g.colsum = w.sqkv; g.stats_in = e->stats; g.n_partials = np;
+    g.out = e->QKV; g.ldo = 3 * D; g.epi = EPI_LN_BIAS_BF16;
     if (int rc = launch_gemm(g, st)) return rc;
-    if (int rc = launch_attention(e->QKV, n_seq, S, heads, causal, kmask, e->Xn, st)) return rc;
+    if (int rc = launch_attention(e->QKV, n_seq, S, heads, causal, kmask, e->AO, st)) return rc;
     g = GemmArgs();
-    g.A = e->Xn; g.lda = D; g.W = w.wo; g.ldw = D; g.M = (int)M; g.N = D; g.K = D;
+    g.A = e->AO; g.lda = D; g.W = w.wo; g.ldw = D; g.M = (int)M; g.N = D; g.K = D;
     g.bias = w.bo; g.out = e->X; g.ldo = D; g.epi = EPI_BIAS_RESID_F32;
+    g.xb_out = e->Xn; g.stats_out = e->stats; g.n_tiles_used = &np;
     if (int rc = launch_gemm(g, st)) return rc;
     // x = x + fc2(quick_gelu(fc1(LN2(x))))                                TF:modeling_clip.py:379-382
-    if (int rc = launch_layernorm(e->X, nullptr, D, M, D, w.ln2_g, w.ln2_b, nullptr, e->Xn, st)) return rc;
     g = GemmArgs();
     g.A = e->Xn; g.lda = D; g.W = w.w1; g.ldw = D; g.M = (int)M; g.N = FF; g.K = D;
-    g.bias = w.b1; g.out = e->H; g.ldo = FF; g.epi = EPI_BIAS_GELU_BF16;
+    g.bias = w.b1; g.colsum = w.s1; g.stats_in = e->stats; g.n_partials = np;
+    g.out = e->H; g.ldo = FF; g.epi = EPI_LN_BIAS_GELU_BF16;
     if (int rc = launch_gemm(g, st)) return rc;
     g = GemmArgs();
     g.A = e->H; g.lda = FF; g.W = w.w2; g.ldw = FF; g.M = (int)M; g.N = D; g.K = FF;
     g.bias = w.b2; g.out = e->X; g.ldo = D; g.epi = EPI_BIAS_RESID_F32;
+    if (l + 1 < num_layers) {  // the last layer's output only feeds the pooled-row LayerNorm (fp32 X)
+      g.xb_out = e->Xn; g.stats_out = e->stats; g.n_tiles_used = &np;
+    }
     if (int rc = launch_gemm(g, st)) return rc;
   }
   return 0;
@@ -374,6 +386,8 @@ PLIP_API int plip_create(const void* host_blob, uint64_t nbytes, float logit_sca
   }
   e->X = reinterpret_cast<float*>(ws + w.x);
   e->Xn = reinterpret_cast<__nv_bfloat16*>(ws + w.xn);
+  e->AO = reinterpret_cast<__nv_bfloat16*>(ws + w.ao);
+  e->stats = reinterpret_cast<float2*>(ws + w.stats);
   e->QKV = reinterpret_cast<__nv_bfloat16*>(ws + w.qkv);
   e->H = reinterpret_cast<__nv_bfloat16*>(ws + w.h);
   e->pooled = reinterpret_cast<__nv_bfloat16*>(ws + w.pooled);
@@ -550,14 +564,22 @@ PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int i
 // ---- per-kernel test hooks ------------------------------------------------------------------------
 PLIP_API int plip_dbg_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K,
                            const float* bias, void* out, int ldo, const float* pos, int epilogue, int cta_group,
-                           int block_n, void* stream) {
+                           int block_n, const float* colsum, const float* stats_in, int n_partials, void* xb_out,
+                           float* stats_out, void* stream) {
   GemmArgs g;
   g.A = static_cast<const __nv_bfloat16*>(A_bf16); g.lda = lda;
   g.W = static_cast<const __nv_bfloat16*>(W_bf16); g.ldw = ldw;
   g.M = M; g.N = N; g.K = K;
   g.bias = bias; g.out = out; g.ldo = ldo; g.pos = pos; g.epi = epilogue;
+  g.colsum = colsum; g.stats_in = reinterpret_cast<const float2*>(stats_in); g.n_partials = n_partials;
+  g.xb_out = static_cast<__nv_bfloat16*>(xb_out); g.stats_out = reinterpret_cast<float2*>(stats_out);
   g.force_cg = cta_group; g.force_bn = block_n;
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+PLIP_API int plip_dbg_rowstats_cast(const float* x, int64_t rows, int dim, void* xb_bf16, float* stats, void* stream) {
+  return launch_rowstats_cast(x, rows, dim, static_cast<__nv_bfloat16*>(xb_bf16), reinterpret_cast<float2*>(stats),
+                              static_cast<cudaStream_t>(stream));
 }
 
 PLIP_API int plip_dbg_layernorm(const float* x, int64_t rows, int dim, int64_t in_row_stride, const float* gamma,

@@ -11,8 +11,15 @@ enum GemmEpilogue : int {
   EPI_BIAS_RESID_F32 = 2,  // x_f32   += acc + bias  (in place)         (out_proj / fc2 + residual, :334,:377,:350,:382)
   EPI_PATCH_F32 = 3,       // x_f32[b*50+1+p] = acc + pos[1+p]          (patch conv + position embedding, :209-217)
   EPI_F32 = 4,             // out_f32 = acc                             (visual/text projection, :861,:823)
-  EPI_COUNT = 5
+  // LayerNorm folded into the consuming GEMM: A holds bf16(x) (un-normalised), W holds
+  // bf16(gamma o W), colsum[n] = sum_k W'[n,k], bias' = bias + W beta, and per-row (sum, sum of squares)
+  // partials of x come from the producing residual GEMM:  out = rstd_r (acc - mean_r colsum_n) + bias'_n.
+  EPI_LN_BIAS_BF16 = 5,       // layer_norm1 + q/k/v projection            (TF:371, 310-312)
+  EPI_LN_BIAS_GELU_BF16 = 6,  // layer_norm2 + fc1 + QuickGELU             (TF:380, 348-349)
+  EPI_COUNT = 7
 };
+
+constexpr int kStatSlots = 4;  // per-row partial statistics slots (one per N tile of the producing GEMM)
 
 struct GemmArgs {
   const __nv_bfloat16* A = nullptr;  // [M, K] row-major, row stride lda elements
@@ -24,6 +31,12 @@ struct GemmArgs {
   void* out = nullptr;               // bf16 or fp32 depending on epilogue; row stride ldo elements
   int ldo = 0;
   const float* pos = nullptr;        // EPI_PATCH_F32: vision position embedding [50, N]
+  const float* colsum = nullptr;     // EPI_LN_*: [N] row sums of the folded bf16 weight
+  const float2* stats_in = nullptr;  // EPI_LN_*: [M, kStatSlots] partial (sum, sumsq) of the fp32 rows behind A
+  int n_partials = 0;                // EPI_LN_*: valid slots in stats_in
+  __nv_bfloat16* xb_out = nullptr;   // EPI_BIAS_RESID_F32 (optional): bf16 copy of the updated rows, stride ldo
+  float2* stats_out = nullptr;       // EPI_BIAS_RESID_F32 (optional): [M, kStatSlots], slot = N-tile index
+  int* n_tiles_used = nullptr;       // out (host): number of N tiles (= stats slots written)
   int epi = EPI_F32;
   int force_cg = 0;                  // 0 = auto; 1 / 2 = CTA-group size (test hook)
   int force_bn = 0;                  // 0 = auto; 128 / 256 = N tile (test hook)

@@ -39,7 +39,7 @@ struct Cfg {
   static constexpr int LOAD_N = BN / CG;  // W rows staged by each CTA
   static constexpr uint32_t B_STAGE = LOAD_N * BK * 2;
   static constexpr uint32_t STAGE = A_STAGE + B_STAGE;
-  static constexpr uint32_t EPI_BYTES = 4 * 32 * 128 + 2 * BN * 4;  // 4 warp staging blocks + 2 bias tiles
+  static constexpr uint32_t EPI_BYTES = 4 * 32 * 128 + 4 * BN * 4;  // 4 warp staging blocks + 2 bias + 2 colsum tiles
   static constexpr int kMaxStages = (227 * 1024 - 1024 - 512 - EPI_BYTES) / STAGE;
   static constexpr int STAGES = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
@@ -52,6 +52,11 @@ struct GemmDev {
   void* out;
   int ldo;
   const float* pos;
+  const float* colsum;
+  const float2* stats_in;
+  int n_partials;
+  __nv_bfloat16* xb_out;
+  float2* stats_out;
 };
 
 // ---- epilogue ---------------------------------------------------------------------------------
@@ -76,8 +81,10 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 }
 
 // acc (+ bias from the smem bias tile) for 32 consecutive columns of this thread's row.
-template <bool HAS_BIAS>
-__device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, float (&f)[32]) {
+// LN_FOLD: rstd * (acc - mean * colsum) + bias', colsum tile stored BN floats after the bias tile pair.
+template <bool HAS_BIAS, bool LN_FOLD, int BN>
+__device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, float mean, float rstd,
+                                           float (&f)[32]) {
   uint32_t v[32];
   tmem_ld32(taddr, v);
   tmem_ld_wait();
@@ -85,19 +92,46 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, f
   for (int i = 0; i < 8; ++i) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (HAS_BIAS) b = ld_shared_f4(bias_smem + 16 * i);  // broadcast read
-    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
-    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
-    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
-    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+    if constexpr (LN_FOLD) {
+      const float4 cs = ld_shared_f4(bias_smem + 2 * BN * 4 + 16 * i);
+      f[4 * i + 0] = fmaf(rstd, fmaf(-mean, cs.x, __uint_as_float(v[4 * i + 0])), b.x);
+      f[4 * i + 1] = fmaf(rstd, fmaf(-mean, cs.y, __uint_as_float(v[4 * i + 1])), b.y);
+      f[4 * i + 2] = fmaf(rstd, fmaf(-mean, cs.z, __uint_as_float(v[4 * i + 2])), b.z);
+      f[4 * i + 3] = fmaf(rstd, fmaf(-mean, cs.w, __uint_as_float(v[4 * i + 3])), b.w);
+    } else {
+      f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
+      f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+      f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
+      f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+    }
   }
 }
 
 // One accumulator tile (this warp's 32 rows x BN columns) -> global memory.
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_row_base, uint32_t stage_smem,
-                                              uint32_t bias_smem, int row_base, int col_base, int lane) {
-  constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32);
-  constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
+                                              uint32_t bias_smem, int row_base, int col_base, int n_blk, int lane) {
+  constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
+  constexpr bool GELU = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
+  constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD);
+  constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || LN_FOLD);
+  float mean = 0.f, rstd = 1.f;
+  if constexpr (LN_FOLD) {
+    // LayerNorm statistics of this thread's row, from the partials the producing GEMM left (fixed order:
+    // bitwise reproducible).  var = E[x^2] - mean^2 in fp32 (TF:371,380 semantics, eps = 1e-5).
+    const int grow = row_base + lane;
+    float s1 = 0.f, s2 = 0.f;
+    if (grow < p.M) {
+      for (int j = 0; j < p.n_partials; ++j) {
+        const float2 t = p.stats_in[static_cast<size_t>(grow) * kStatSlots + j];
+        s1 += t.x;
+        s2 += t.y;
+      }
+    }
+    const float inv_k = 1.0f / static_cast<float>(p.K);
+    mean = s1 * inv_k;
+    rstd = rsqrtf(fmaxf(s2 * inv_k - mean * mean, 0.f) + kLnEps);
+  }
   const uint32_t my_row = stage_smem + lane * 128;
   const int sw = lane & 7;
   const int rb_row = lane >> 3;  // read-back: row within a group of 4
@@ -110,8 +144,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float f[32];
-        load_acc32<HAS_BIAS>(tmem_row_base + blk * 64 + half * 32, bias_smem + (blk * 64 + half * 32) * 4, f);
-        if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+        load_acc32<HAS_BIAS, LN_FOLD, BN>(tmem_row_base + blk * 64 + half * 32, bias_smem + (blk * 64 + half * 32) * 4,
+                                          mean, rstd, f);
+        if constexpr (GELU) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
         }
@@ -136,6 +171,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
       __syncwarp();
     }
   } else {
+    // per-row (sum, sum of squares) of the updated residual rows this lane writes (rows i*4 + rb_row)
+    float st1[8], st2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st1[i] = st2[i] = 0.f;
+    const bool emit = (EPI == EPI_BIAS_RESID_F32) && p.xb_out != nullptr;
 #pragma unroll 1
     for (int blk = 0; blk < BN / 32; ++blk) {
       // 32 columns -> 128 B of fp32 per row
@@ -154,7 +194,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
       }
       {
         float f[32];
-        load_acc32<HAS_BIAS>(tmem_row_base + blk * 32, bias_smem + blk * 32 * 4, f);
+        load_acc32<HAS_BIAS, false, BN>(tmem_row_base + blk * 32, bias_smem + blk * 32 * 4, 0.f, 1.f, f);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           st_shared_v4(my_row + ((c ^ sw) << 4), __float_as_uint(f[4 * c + 0]), __float_as_uint(f[4 * c + 1]),
@@ -168,8 +208,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
         const int grow = row_base + r;
         if (grow < p.M) {
           if constexpr (EPI == EPI_BIAS_RESID_F32) {
-            *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldo + col) =
-                make_float4(xr[i].x + v.x, xr[i].y + v.y, xr[i].z + v.z, xr[i].w + v.w);
+            const float4 y = make_float4(xr[i].x + v.x, xr[i].y + v.y, xr[i].z + v.z, xr[i].w + v.w);
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldo + col) = y;
+            if (emit) {
+              // bf16 copy (A operand of the next, LayerNorm-folded GEMM) + statistics of the fp32 row
+              uint2 u;
+              u.x = pack_bf16x2(y.x, y.y);
+              u.y = pack_bf16x2(y.z, y.w);
+              *reinterpret_cast<uint2*>(p.xb_out + static_cast<size_t>(grow) * p.ldo + col) = u;
+              st1[i] += (y.x + y.y) + (y.z + y.w);
+              st2[i] += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+            }
           } else if constexpr (EPI == EPI_PATCH_F32) {
             const int b = grow / kPatches;
             const int pp = grow - b * kPatches;
@@ -182,6 +231,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
         }
       }
       __syncwarp();
+    }
+    if constexpr (EPI == EPI_BIAS_RESID_F32) {
+      if (emit) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = st1[i], b = st2[i];
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {  // the 8 lanes that share a row
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          const int grow = row_base + i * 4 + rb_row;
+          if (rb_chunk == 0 && grow < p.M)
+            p.stats_out[static_cast<size_t>(grow) * kStatSlots + n_blk] = make_float2(a, b);
+        }
+      }
     }
   }
 }
@@ -297,7 +362,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32);
+    constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
+    constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD);
     const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
     const int etid = threadIdx.x - 128;
     int a = 0;
@@ -307,7 +373,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if constexpr (HAS_BIAS) {
         // bias tile for this accumulator stage (its previous readers are two tiles behind us)
         float* bs = reinterpret_cast<float*>(smem_raw + (bias_base - smem_raw_u32)) + a * BN;
-        for (int i = etid; i < BN; i += 128) bs[i] = __ldg(p.bias + n_blk * BN + i);
+        for (int i = etid; i < BN; i += 128) {
+          bs[i] = __ldg(p.bias + n_blk * BN + i);
+        }
+        if constexpr (LN_FOLD) {
+          float* cs = reinterpret_cast<float*>(smem_raw + (bias_base - smem_raw_u32)) + 2 * BN + a * BN;
+          for (int i = etid; i < BN; i += 128) cs[i] = __ldg(p.colsum + n_blk * BN + i);
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       const int row_base = m_blk * BM * CG + cta_rank * BM + q * 32;
@@ -329,7 +401,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      epilogue_tile<BN, EPI>(p, trow, epi_base + q * kEpiStageBytes, bias_base + a * BN * 4, row_base, n_blk * BN, lane);
+      epilogue_tile<BN, EPI>(p, trow, epi_base + q * kEpiStageBytes, bias_base + a * BN * 4, row_base, n_blk * BN, n_blk,
+                             lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -401,6 +474,9 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   GemmDev p;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.bias = g.bias; p.out = g.out; p.ldo = g.ldo; p.pos = g.pos;
+  p.colsum = g.colsum; p.stats_in = g.stats_in; p.n_partials = g.n_partials;
+  p.xb_out = g.xb_out; p.stats_out = g.stats_out;
+  if (g.n_tiles_used) *g.n_tiles_used = g.N / BN;
 
   const int num_tiles = ((g.M + BM * CG - 1) / (BM * CG)) * (g.N / BN);
   int groups = max_groups;
@@ -419,6 +495,8 @@ int launch_epi(const GemmArgs& g, cudaStream_t stream) {
     case EPI_BIAS_RESID_F32: return launch_inst<CG, BN, EPI_BIAS_RESID_F32>(g, stream);
     case EPI_PATCH_F32: return launch_inst<CG, BN, EPI_PATCH_F32>(g, stream);
     case EPI_F32: return launch_inst<CG, BN, EPI_F32>(g, stream);
+    case EPI_LN_BIAS_BF16: return launch_inst<CG, BN, EPI_LN_BIAS_BF16>(g, stream);
+    case EPI_LN_BIAS_GELU_BF16: return launch_inst<CG, BN, EPI_LN_BIAS_GELU_BF16>(g, stream);
     default: set_last_error("launch_gemm: bad epilogue %d", g.epi); return -2;
   }
 }
@@ -428,19 +506,31 @@ int launch_epi(const GemmArgs& g, cudaStream_t stream) {
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   PLIP_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "launch_gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   PLIP_REQUIRE(g.K % BK == 0, "launch_gemm: K=%d must be a multiple of %d", g.K, BK);
-  PLIP_REQUIRE(g.N % 128 == 0 || (g.N % 192 == 0 && g.force_bn == 192), "launch_gemm: N=%d must be a multiple of 128", g.N);
+  PLIP_REQUIRE(g.N % 128 == 0 || g.N % 192 == 0, "launch_gemm: N=%d must be a multiple of 128 or 192", g.N);
   PLIP_REQUIRE((g.lda % 8) == 0 && (g.ldw % 8) == 0 && (g.ldo % 8) == 0,
                "launch_gemm: leading dimensions must be multiples of 8 elements");
   PLIP_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.W) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(g.out) & 15) == 0,
                "launch_gemm: operands must be 16-byte aligned");
+  if (g.epi == EPI_LN_BIAS_BF16 || g.epi == EPI_LN_BIAS_GELU_BF16)
+    PLIP_REQUIRE(g.colsum && g.stats_in && g.bias && g.n_partials >= 1 && g.n_partials <= kStatSlots,
+                 "launch_gemm: LayerNorm-folded epilogue needs colsum, stats and 1..%d partials", kStatSlots);
+  if (g.xb_out || g.stats_out)
+    PLIP_REQUIRE(g.epi == EPI_BIAS_RESID_F32 && g.xb_out && g.stats_out,
+                 "launch_gemm: xb/stats outputs belong to the residual epilogue");
   static const int env_cg = env_int("PLIP_GEMM_CG", 0);
   static const int env_bn = env_int("PLIP_GEMM_BN", 0);
   int cg = g.force_cg ? g.force_cg : (env_cg ? env_cg : 2);
   int bn = g.force_bn ? g.force_bn : (env_bn ? env_bn : 256);
+  // Memory-bound residual GEMM with a short K (out_proj): 192-wide tiles quantise better on 74 CTA
+  // pairs (800 tiles = 10.8 waves instead of 600 = 8.1 -> 9) and were measured 7 % faster (exp8).
+  if (!g.force_bn && !env_bn && cg == 2 && g.epi == EPI_BIAS_RESID_F32 && g.K <= 1024 && g.N % 192 == 0)
+    bn = 192;
   if (g.N % bn != 0) bn = 128;
   PLIP_REQUIRE((cg == 1 || cg == 2) && (bn == 128 || bn == 256 || (bn == 192 && cg == 2)),
                "launch_gemm: bad config cg=%d bn=%d", cg, bn);
+  PLIP_REQUIRE(!g.stats_out || g.N / bn <= kStatSlots, "launch_gemm: N=%d / BN=%d exceeds %d statistics slots", g.N, bn,
+               kStatSlots);
   if (cg == 1) return bn == 256 ? launch_epi<1, 256>(g, stream) : launch_epi<1, 128>(g, stream);
   if (bn == 192) return launch_epi<2, 192>(g, stream);
   return bn == 256 ? launch_epi<2, 256>(g, stream) : launch_epi<2, 128>(g, stream);

@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace plip {
@@ -17,6 +18,14 @@ void set_last_error(const char* fmt, ...) {
 }
 
 const char* get_last_error() { return g_last_error; }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("PLIP_PDL");
+    return v != nullptr && v[0] == '1';
+  }();
+  return on;
+}
 
 // cuTensorMapEncodeTiled is a driver-API symbol; resolve it through the runtime so the library
 // does not link against libcuda.so (absent on the build box).

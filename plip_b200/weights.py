@@ -9,6 +9,10 @@ as the way weights reach the device.  The blob layout is owned by the CUDA libra
 * q/k/v projections are concatenated to one ``[3D, D]`` matrix and the q rows (weight and bias) are
   pre-multiplied by ``head_dim ** -0.5 = 0.125`` (exact: power of two), which is the scale HF applies
   inside the attention core (TF:modeling_clip.py:291,322);
+* ``layer_norm1`` / ``layer_norm2`` (TF:371,380) are folded into the GEMM that consumes them:
+  ``LN(x) W^T + b = rstd (x (gamma o W)^T - mean colsum) + (b + W beta)`` with
+  ``colsum[n] = sum_k bf16(gamma o W)[n,k]``; the device keeps ``bf16(gamma o W)``, ``colsum`` and the
+  adjusted bias, never the LayerNorm parameters themselves;
 * the conv patch embedding ``[768,3,32,32]`` is viewed as ``[768, 3072]`` (c, ky, kx order).
 """
 from __future__ import annotations
@@ -92,14 +96,40 @@ def pack_state_dict(state_dict: Mapping[str, torch.Tensor]) -> Tuple[torch.Tenso
     sd = normalize_state_dict(state_dict)
     L = lib()
     blob = torch.zeros(int(L.plip_weights_blob_bytes()), dtype=torch.uint8)
+    folded = {}  # (base name, "weight"/"bias"/"colsum") -> fp32 tensor, computed once per projection
+
+    def fold(base: str, flags: int):
+        """base = '<layer>.self_attn.q_proj' or '<layer>.mlp.fc1' -> folded weight / bias / colsum."""
+        if (base, "weight") in folded:
+            return
+        if flags & 1:
+            ws, bs = [], []
+            for i, n in enumerate(("q_proj", "k_proj", "v_proj")):
+                w = sd[base.replace("q_proj", n) + ".weight"].detach().to(torch.float32)
+                b = sd[base.replace("q_proj", n) + ".bias"].detach().to(torch.float32)
+                ws.append(w * HEAD_SCALE if i == 0 else w)
+                bs.append(b * HEAD_SCALE if i == 0 else b)
+            w, b = torch.cat(ws, dim=0), torch.cat(bs, dim=0)
+        else:
+            w = sd[base + ".weight"].detach().to(torch.float32)
+            b = sd[base + ".bias"].detach().to(torch.float32)
+        if flags & 2:
+            layer = base.rsplit(".", 2)[0]                      # "...encoder.layers.N"
+            ln = layer + (".layer_norm1" if "q_proj" in base else ".layer_norm2")
+            gamma = sd[ln + ".weight"].detach().to(torch.float32)
+            beta = sd[ln + ".bias"].detach().to(torch.float32)
+            b = b + w @ beta
+            w = (w * gamma[None, :]).to(torch.bfloat16).to(torch.float32)
+        folded[(base, "weight")] = w
+        folded[(base, "bias")] = b
+        folded[(base, "colsum")] = w.to(torch.bfloat16).to(torch.float32).sum(dim=1)
+
     for ti in tensor_table():
         name = ti.name.decode()
         if ti.fused:
-            parts = []
-            for i, n in enumerate(("q_proj", "k_proj", "v_proj")):
-                t = sd[name.replace("q_proj", n)].detach().to(torch.float32)
-                parts.append(t * HEAD_SCALE if i == 0 else t)
-            t = torch.cat(parts, dim=0)
+            base, kind = name.rsplit(".", 1)
+            fold(base, ti.fused)
+            t = folded[(base, kind)]
         else:
             if name not in sd:
                 raise KeyError(f"missing weight {name!r}")

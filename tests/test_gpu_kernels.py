@@ -71,16 +71,63 @@ def test_gemm_epilogues(L, cg, bn, epi, M, N, K):
         out = torch.zeros(M, N, device=dev)
         tol = 2e-4
     _check(L.plip_dbg_gemm(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), out.data_ptr(), N,
-                           pos.data_ptr(), epi, cg, bn, _stream()), "gemm")
+                           pos.data_ptr(), epi, cg, bn, None, None, 0, None, None, _stream()), "gemm")
     torch.cuda.synchronize()
     assert (out.float() - ref).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("D,N,gelu,bn_prod", [(768, 2304, False, 256), (768, 3072, True, 192), (512, 1536, False, 256),
+                                               (512, 2048, True, 128)])
+def test_layernorm_folded_gemm_chain(L, D, N, gelu, bn_prod):
+    """Residual GEMM epilogue emits bf16(x') + row statistics; the next GEMM applies LayerNorm through the
+    fold  rstd (x' W'^T - mean colsum) + bias'  ==  LN(x') W^T + bias   (TF:371/380 + 310-312/348-349)."""
+    dev = "cuda"
+    M, K0 = 1000, 256
+    g = torch.Generator().manual_seed(D + N)
+    A0 = (torch.randn(M, K0, generator=g) * 0.5).to(dev).to(torch.bfloat16)
+    W0 = (torch.randn(D, K0, generator=g) * 0.1).to(dev).to(torch.bfloat16)
+    b0 = torch.randn(D, generator=g).to(dev) * 0.1
+    x0 = (torch.randn(M, D, generator=g) * 1.5 + 0.4).to(dev)
+    x = x0.clone()
+    xb = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
+    stats = torch.full((M, 4, 2), float("nan"), device=dev)
+    _check(L.plip_dbg_gemm(A0.data_ptr(), K0, W0.data_ptr(), K0, M, D, K0, b0.data_ptr(), x.data_ptr(), D, None, 2, 2,
+                           bn_prod, None, None, 0, xb.data_ptr(), stats.data_ptr(), _stream()), "resid gemm")
+    xr = x0 + A0.float() @ W0.float().t() + b0
+    npart = D // bn_prod
+    assert (x - xr).abs().max().item() < 2e-4
+    assert torch.equal(xb, x.to(torch.bfloat16))
+    s = stats[:, :npart].sum(1)
+    assert torch.allclose(s[:, 0], x.sum(-1), atol=2e-3) and torch.allclose(s[:, 1], (x * x).sum(-1), rtol=1e-5, atol=1e-2)
+    # standalone producer of the same quantities (start of a tower)
+    xb2 = torch.zeros_like(xb)
+    st2 = torch.zeros(M, 4, 2, device=dev)
+    _check(L.plip_dbg_rowstats_cast(x.data_ptr(), M, D, xb2.data_ptr(), st2.data_ptr(), _stream()), "rowstats")
+    assert torch.equal(xb2, xb) and torch.allclose(st2[:, 0, 0], x.sum(-1), atol=2e-3)
+    # consumer with the fold
+    gam = 1 + 0.1 * torch.randn(D, generator=g).to(dev)
+    bet = 0.05 * torch.randn(D, generator=g).to(dev)
+    W = (torch.randn(N, D, generator=g) * 0.05).to(dev)
+    bias = torch.randn(N, generator=g).to(dev) * 0.1
+    Wf = (W * gam[None]).to(torch.bfloat16)
+    colsum = Wf.float().sum(1).contiguous()
+    biasf = (bias + W @ bet).contiguous()
+    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    _check(L.plip_dbg_gemm(xb.data_ptr(), D, Wf.data_ptr(), D, M, N, D, biasf.data_ptr(), out.data_ptr(), N, None,
+                           6 if gelu else 5, 0, 0, colsum.data_ptr(), stats.data_ptr(), npart, None, None, _stream()), "ln gemm")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (D,), gam, bet, 1e-5) @ W.t() + bias
+    if gelu:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    err = (out.float() - ref).abs()
+    assert err.max().item() < 0.06 and err.mean().item() < 6e-3, (err.max().item(), err.mean().item())
 
 
 def test_gemm_rejects_bad_shapes(L):
     a = torch.zeros(128, 100, device="cuda", dtype=torch.bfloat16)
     o = torch.zeros(128, 128, device="cuda")
     assert L.plip_dbg_gemm(a.data_ptr(), 100, a.data_ptr(), 100, 128, 128, 100, None, o.data_ptr(), 128, None, 4, 0, 0,
-                           _stream()) != 0
+                           None, None, 0, None, None, _stream()) != 0
     from plip_b200._lib import last_error
     assert "multiple of 64" in last_error()
 

@@ -13,22 +13,43 @@ def test_pack_layout_and_values(state_dict):
     blob, scale = W.pack_state_dict(state_dict)
     assert abs(scale - float(state_dict["logit_scale"].exp())) < 1e-6
     table = {ti.name.decode(): ti for ti in W.tensor_table()}
-    ti = table["vision_model.encoder.layers.3.mlp.fc1.weight"]
-    assert (ti.rows, ti.cols, ti.dtype) == (3072, 768, 1)
-    ref = state_dict["vision_model.encoder.layers.3.mlp.fc1.weight"].to(torch.bfloat16)
-    assert torch.equal(_view(blob, ti), ref)
-    # fused q|k|v with the 0.125 head scale folded into q (exact in bf16: power of two)
+    # plain GEMM weight: one RNE rounding to bf16
+    ti = table["vision_model.encoder.layers.3.mlp.fc2.weight"]
+    assert (ti.rows, ti.cols, ti.dtype, ti.fused) == (768, 3072, 1, 0)
+    assert torch.equal(_view(blob, ti), state_dict["vision_model.encoder.layers.3.mlp.fc2.weight"].to(torch.bfloat16))
+    # fc1 with layer_norm2 folded in: W' = bf16(gamma o W), bias' = bias + W beta, colsum = rowsum(W')
+    L = "vision_model.encoder.layers.3."
+    ti = table[L + "mlp.fc1.weight"]
+    assert (ti.rows, ti.cols, ti.dtype, ti.fused) == (3072, 768, 1, 2)
+    w, b = state_dict[L + "mlp.fc1.weight"], state_dict[L + "mlp.fc1.bias"]
+    g, be = state_dict[L + "layer_norm2.weight"], state_dict[L + "layer_norm2.bias"]
+    wf = (w * g[None]).to(torch.bfloat16)
+    assert torch.equal(_view(blob, ti), wf)
+    assert torch.allclose(_view(blob, table[L + "mlp.fc1.bias"]).flatten(), b + w @ be, atol=1e-6)
+    assert torch.allclose(_view(blob, table[L + "mlp.fc1.colsum"]).flatten(), wf.float().sum(1), atol=1e-5)
+    assert L + "layer_norm2.weight" not in table and L + "layer_norm1.bias" not in table
+    # the fold is exact algebra: LN(x) W^T + b == rstd (x W'^T - mean colsum) + bias'  (fp32 check)
+    x = torch.randn(5, 768) * 2 + 0.3
+    ref = torch.nn.functional.layer_norm(x, (768,), g, be, 1e-5) @ w.t() + b
+    mean = x.mean(-1, keepdim=True)
+    rstd = torch.rsqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5)
+    wg = w * g[None]
+    assert torch.allclose(rstd * (x @ wg.t() - mean * wg.sum(1)) + (b + w @ be), ref, atol=2e-4)
+    # fused q|k|v: 0.125 head scale on the q rows (exact: power of two) + layer_norm1 fold
     ti = table["text_model.encoder.layers.0.self_attn.q_proj.weight"]
-    assert (ti.rows, ti.cols, ti.fused) == (1536, 512, 1)
+    assert (ti.rows, ti.cols, ti.fused) == (1536, 512, 3)
     p = "text_model.encoder.layers.0.self_attn."
+    g1 = state_dict["text_model.encoder.layers.0.layer_norm1.weight"]
+    be1 = state_dict["text_model.encoder.layers.0.layer_norm1.bias"]
     fused = _view(blob, ti)
-    assert torch.equal(fused[:512], (state_dict[p + "q_proj.weight"] * 0.125).to(torch.bfloat16))
-    assert torch.equal(fused[:512].float() * 8, state_dict[p + "q_proj.weight"].to(torch.bfloat16).float())
-    assert torch.equal(fused[512:1024], state_dict[p + "k_proj.weight"].to(torch.bfloat16))
-    assert torch.equal(fused[1024:], state_dict[p + "v_proj.weight"].to(torch.bfloat16))
-    tb = table["text_model.encoder.layers.0.self_attn.q_proj.bias"]
-    b = _view(blob, tb).flatten()
-    assert torch.equal(b[:512], state_dict[p + "q_proj.bias"] * 0.125) and torch.equal(b[512:1024], state_dict[p + "k_proj.bias"])
+    assert torch.equal(fused[:512], (state_dict[p + "q_proj.weight"] * 0.125 * g1[None]).to(torch.bfloat16))
+    assert torch.equal(fused[512:1024], (state_dict[p + "k_proj.weight"] * g1[None]).to(torch.bfloat16))
+    assert torch.equal(fused[1024:], (state_dict[p + "v_proj.weight"] * g1[None]).to(torch.bfloat16))
+    bq = _view(blob, table[p + "q_proj.bias"]).flatten()
+    assert torch.allclose(bq[:512], 0.125 * (state_dict[p + "q_proj.bias"] + state_dict[p + "q_proj.weight"] @ be1), atol=1e-6)
+    assert torch.allclose(bq[512:1024], state_dict[p + "k_proj.bias"] + state_dict[p + "k_proj.weight"] @ be1, atol=1e-6)
+    cs = _view(blob, table[p + "q_proj.colsum"]).flatten()
+    assert torch.allclose(cs, fused.float().sum(1), atol=1e-5)
     # conv patch embedding viewed as [768, 3*32*32]
     ti = table["vision_model.embeddings.patch_embedding.weight"]
     assert torch.equal(_view(blob, ti), state_dict["vision_model.embeddings.patch_embedding.weight"].reshape(768, 3072).to(torch.bfloat16))

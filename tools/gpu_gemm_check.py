@@ -62,7 +62,7 @@ def run_case(cg, bn, epi, M, N, K):
 
     def call():
         check(L.plip_dbg_gemm(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), out.data_ptr(), N,
-                              pos.data_ptr(), epi, cg, bn, stream), "gemm")
+                              pos.data_ptr(), epi, cg, bn, None, None, 0, None, None, stream), "gemm")
     call()
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
