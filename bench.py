@@ -177,7 +177,7 @@ def kernel_rooflines(eng, peaks, stream):
     shapes = [("ln1+qkv", 5, 2304, 768), ("out_proj+resid", 2, 768, 768), ("ln2+fc1+gelu", 6, 3072, 768),
               ("fc2+resid", 2, 768, 3072)]
     res = []
-    stats = torch.zeros(M, 4, 2, device="cuda")
+    stats = torch.zeros(M, 8, 2, device="cuda")
     stats[:, 0, 1] = 768.0                                   # mean 0, var 1 -> rstd ~ 1
     for name, epi, N, K in shapes:
         A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
@@ -186,7 +186,7 @@ def kernel_rooflines(eng, peaks, stream):
         colsum = W.float().sum(1).contiguous()
         out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if epi == 2 else torch.bfloat16)
         xb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if epi == 2 else None
-        st_out = torch.empty(M, 4, 2, device="cuda") if epi == 2 else None
+        st_out = torch.empty(M, 8, 2, device="cuda") if epi == 2 else None
         call = lambda: check(L.plip_dbg_gemm(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), out.data_ptr(), N,  # noqa: E731
                                              None, epi, 0, 0, colsum.data_ptr() if epi >= 5 else None,
                                              stats.data_ptr() if epi >= 5 else None, 1 if epi >= 5 else 0,

@@ -136,8 +136,8 @@ PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int i
 
 /* ---- per-kernel test hooks (used by tests/ only; stream-ordered, device pointers) ------------ */
 /* epilogue: 0 bias->bf16, 1 bias+QuickGELU->bf16, 2 x_f32 += acc+bias (optionally also xb_out bf16 copy +
- * stats_out [M,4,2] row statistics), 3 patch scatter + pos, 4 plain f32, 5/6 = 0/1 with the LayerNorm fold
- * (colsum [N], stats_in [M,4,2] with n_partials valid slots). */
+ * stats_out [M,8,2] row statistics), 3 patch scatter + pos, 4 plain f32, 5/6 = 0/1 with the LayerNorm fold
+ * (colsum [N], stats_in [M,8,2] with n_partials valid slots). */
 PLIP_API int plip_dbg_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K,
                            const float* bias, void* out, int ldo, const float* pos, int epilogue, int cta_group,
                            int block_n, const float* colsum, const float* stats_in, int n_partials, void* xb_out,

@@ -19,7 +19,7 @@ enum GemmEpilogue : int {
   EPI_COUNT = 7
 };
 
-constexpr int kStatSlots = 4;  // per-row partial statistics slots (one per N tile of the producing GEMM)
+constexpr int kStatSlots = 8;  // per-row partial statistics slots (two per N tile of the producing GEMM: one per epilogue warp half)
 
 struct GemmArgs {
   const __nv_bfloat16* A = nullptr;  // [M, K] row-major, row stride lda elements
@@ -36,7 +36,7 @@ struct GemmArgs {
   int n_partials = 0;                // EPI_LN_*: valid slots in stats_in
   __nv_bfloat16* xb_out = nullptr;   // EPI_BIAS_RESID_F32 (optional): bf16 copy of the updated rows, stride ldo
   float2* stats_out = nullptr;       // EPI_BIAS_RESID_F32 (optional): [M, kStatSlots], slot = N-tile index
-  int* n_tiles_used = nullptr;       // out (host): number of N tiles (= stats slots written)
+  int* n_tiles_used = nullptr;       // out (host): number of statistics slots written (2 per N tile)
   int epi = EPI_F32;
   int force_cg = 0;                  // 0 = auto; 1 / 2 = CTA-group size (test hook)
   int force_bn = 0;                  // 0 = auto; 128 / 256 = N tile (test hook)

@@ -31,7 +31,9 @@ namespace {
 
 constexpr int BM = 128;  // accumulator rows per CTA (TMEM lanes)
 constexpr int BK = 64;   // k-block: 64 bf16 = 128 B = one swizzle atom
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;      // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;       // two per TMEM lane quarter, splitting the tile's column blocks
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr uint32_t A_STAGE = BM * BK * 2;
 
 template <int CG, int BN>
@@ -39,7 +41,7 @@ struct Cfg {
   static constexpr int LOAD_N = BN / CG;  // W rows staged by each CTA
   static constexpr uint32_t B_STAGE = LOAD_N * BK * 2;
   static constexpr uint32_t STAGE = A_STAGE + B_STAGE;
-  static constexpr uint32_t EPI_BYTES = 4 * 32 * 128 + 4 * BN * 4;  // 4 warp staging blocks + 2 bias + 2 colsum tiles
+  static constexpr uint32_t EPI_BYTES = kEpiWarps * 32 * 128 + 4 * BN * 4;  // per-warp staging blocks + 2 bias + 2 colsum tiles
   static constexpr int kMaxStages = (227 * 1024 - 1024 - 512 - EPI_BYTES) / STAGE;
   static constexpr int STAGES = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
@@ -110,7 +112,8 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, f
 // One accumulator tile (this warp's 32 rows x BN columns) -> global memory.
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_row_base, uint32_t stage_smem,
-                                              uint32_t bias_smem, int row_base, int col_base, int n_blk, int lane) {
+                                              uint32_t bias_smem, int row_base, int col_base, int n_blk, int half,
+                                              int lane) {
   constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   constexpr bool GELU = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD);
@@ -139,7 +142,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
 
   if constexpr (OUT_BF16) {
 #pragma unroll 1
-    for (int blk = 0; blk < BN / 64; ++blk) {
+    for (int blk = half; blk < BN / 64; blk += 2) {
       // 64 columns -> 128 B of bf16 per row
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -177,7 +180,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
     for (int i = 0; i < 8; ++i) st1[i] = st2[i] = 0.f;
     const bool emit = (EPI == EPI_BIAS_RESID_F32) && p.xb_out != nullptr;
 #pragma unroll 1
-    for (int blk = 0; blk < BN / 32; ++blk) {
+    for (int blk = half; blk < BN / 32; blk += 2) {
       // 32 columns -> 128 B of fp32 per row
       const int col = col_base + blk * 32 + rb_chunk * 4;
       float* out = reinterpret_cast<float*>(p.out);
@@ -244,7 +247,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
           }
           const int grow = row_base + i * 4 + rb_row;
           if (rb_chunk == 0 && grow < p.M)
-            p.stats_out[static_cast<size_t>(grow) * kStatSlots + n_blk] = make_float2(a, b);
+            p.stats_out[static_cast<size_t>(grow) * kStatSlots + 2 * n_blk + half] = make_float2(a, b);
         }
       }
     }
@@ -261,7 +264,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t smem_raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + STAGES * C::STAGE;   // 1024-aligned: 4 x 4 KB staging blocks
-  const uint32_t bias_base = epi_base + 4 * kEpiStageBytes;  // 2 x BN floats
+  const uint32_t bias_base = epi_base + kEpiWarps * kEpiStageBytes;  // 2 x BN bias + 2 x BN colsum floats
   const uint32_t bar_base = smem_base + STAGES * C::STAGE + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -285,7 +288,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);        // tcgen05.commit
-      mbar_init(tempty_bar(a), 4 * CG);  // one arrive per epilogue warp (both CTAs of a pair)
+      mbar_init(tempty_bar(a), kEpiWarps * CG);  // one arrive per epilogue warp (both CTAs of a pair)
     }
     fence_mbar_init();
   }
@@ -364,7 +367,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================== epilogue =====================
     constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
     constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD);
-    const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int q = warp & 3;          // the TMEM lane quarter this warp may access (warp % 4)
+    const int half = (warp - 4) >> 2;  // which interleaved half of the tile's column blocks it handles
     const int etid = threadIdx.x - 128;
     int a = 0;
     uint32_t aph = 0;
@@ -373,14 +377,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if constexpr (HAS_BIAS) {
         // bias tile for this accumulator stage (its previous readers are two tiles behind us)
         float* bs = reinterpret_cast<float*>(smem_raw + (bias_base - smem_raw_u32)) + a * BN;
-        for (int i = etid; i < BN; i += 128) {
+        for (int i = etid; i < BN; i += kEpiThreads) {
           bs[i] = __ldg(p.bias + n_blk * BN + i);
         }
         if constexpr (LN_FOLD) {
           float* cs = reinterpret_cast<float*>(smem_raw + (bias_base - smem_raw_u32)) + 2 * BN + a * BN;
-          for (int i = etid; i < BN; i += 128) cs[i] = __ldg(p.colsum + n_blk * BN + i);
+          for (int i = etid; i < BN; i += kEpiThreads) cs[i] = __ldg(p.colsum + n_blk * BN + i);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       const int row_base = m_blk * BM * CG + cta_rank * BM + q * 32;
       if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -392,8 +396,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (grow < p.M) {
 #pragma unroll
             for (int c = 0; c < BN / 256 + (BN % 256 != 0); ++c) {
-              const float* ptr = xin + static_cast<size_t>(grow) * p.ldo + n_blk * BN + c * 256 + (lane & 7) * 32;
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+              const int cofs = c * 256 + (lane & 7) * 32;  // one 128-byte line = one 32-column block
+              const float* ptr = xin + static_cast<size_t>(grow) * p.ldo + n_blk * BN + cofs;
+              if (cofs < BN && (((lane & 7) & 1) == half)) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
             }
           }
         }
@@ -401,8 +406,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      epilogue_tile<BN, EPI>(p, trow, epi_base + q * kEpiStageBytes, bias_base + a * BN * 4, row_base, n_blk * BN, n_blk,
-                             lane);
+      epilogue_tile<BN, EPI>(p, trow, epi_base + (warp - 4) * kEpiStageBytes, bias_base + a * BN * 4, row_base,
+                             n_blk * BN, n_blk, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -476,7 +481,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   p.bias = g.bias; p.out = g.out; p.ldo = g.ldo; p.pos = g.pos;
   p.colsum = g.colsum; p.stats_in = g.stats_in; p.n_partials = g.n_partials;
   p.xb_out = g.xb_out; p.stats_out = g.stats_out;
-  if (g.n_tiles_used) *g.n_tiles_used = g.N / BN;
+  if (g.n_tiles_used) *g.n_tiles_used = 2 * (g.N / BN);
 
   const int num_tiles = ((g.M + BM * CG - 1) / (BM * CG)) * (g.N / BN);
   int groups = max_groups;
@@ -529,8 +534,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (g.N % bn != 0) bn = 128;
   PLIP_REQUIRE((cg == 1 || cg == 2) && (bn == 128 || bn == 256 || (bn == 192 && cg == 2)),
                "launch_gemm: bad config cg=%d bn=%d", cg, bn);
-  PLIP_REQUIRE(!g.stats_out || g.N / bn <= kStatSlots, "launch_gemm: N=%d / BN=%d exceeds %d statistics slots", g.N, bn,
-               kStatSlots);
+  PLIP_REQUIRE(!g.stats_out || 2 * (g.N / bn) <= kStatSlots, "launch_gemm: N=%d / BN=%d exceeds %d statistics slots",
+               g.N, bn, kStatSlots);
   if (cg == 1) return bn == 256 ? launch_epi<1, 256>(g, stream) : launch_epi<1, 128>(g, stream);
   if (bn == 192) return launch_epi<2, 192>(g, stream);
   return bn == 256 ? launch_epi<2, 256>(g, stream) : launch_epi<2, 128>(g, stream);

@@ -90,18 +90,18 @@ def test_layernorm_folded_gemm_chain(L, D, N, gelu, bn_prod):
     x0 = (torch.randn(M, D, generator=g) * 1.5 + 0.4).to(dev)
     x = x0.clone()
     xb = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
-    stats = torch.full((M, 4, 2), float("nan"), device=dev)
+    stats = torch.full((M, 8, 2), float("nan"), device=dev)
     _check(L.plip_dbg_gemm(A0.data_ptr(), K0, W0.data_ptr(), K0, M, D, K0, b0.data_ptr(), x.data_ptr(), D, None, 2, 2,
                            bn_prod, None, None, 0, xb.data_ptr(), stats.data_ptr(), _stream()), "resid gemm")
     xr = x0 + A0.float() @ W0.float().t() + b0
-    npart = D // bn_prod
+    npart = 2 * (D // bn_prod)      # one slot per (N tile, epilogue-warp half)
     assert (x - xr).abs().max().item() < 2e-4
     assert torch.equal(xb, x.to(torch.bfloat16))
     s = stats[:, :npart].sum(1)
     assert torch.allclose(s[:, 0], x.sum(-1), atol=2e-3) and torch.allclose(s[:, 1], (x * x).sum(-1), rtol=1e-5, atol=1e-2)
     # standalone producer of the same quantities (start of a tower)
     xb2 = torch.zeros_like(xb)
-    st2 = torch.zeros(M, 4, 2, device=dev)
+    st2 = torch.zeros(M, 8, 2, device=dev)
     _check(L.plip_dbg_rowstats_cast(x.data_ptr(), M, D, xb2.data_ptr(), st2.data_ptr(), _stream()), "rowstats")
     assert torch.equal(xb2, xb) and torch.allclose(st2[:, 0, 0], x.sum(-1), atol=2e-3)
     # consumer with the fold
