@@ -33,6 +33,13 @@ constexpr uint32_t kTmemCols = 128;
 constexpr uint32_t kColS = 0, kColP = 0, kColO = 64;
 constexpr int kAttCtasPerSm = 4;
 
+// 2^x, flush-to-zero, no range fix-ups: one MUFU op (inputs are <= 0 here, -inf -> +0).
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -206,18 +213,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
           uint32_t v[32];
           tmem_ld32(lane_base + kColS + 32 * j, v);
           tmem_ld_wait();
-          float e[32];
+          const uint32_t vm = valid[j];
+          if (__all_sync(0xffffffffu, vm == 0xffffffffu)) {
+            // every column of this chunk is visible to every row of the warp: no masking work
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float x = exp2f(fmaf(__uint_as_float(v[c]), kLog2e, -mx_s));
-            e[c] = ((valid[j] >> c) & 1u) ? x : 0.f;
-          }
+            for (int c = 0; c < 16; ++c) {
+              const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * c]), kLog2e, -mx_s));
+              const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * c + 1]), kLog2e, -mx_s));
+              sum += e0 + e1;
+              pk[c] = pack_bf16x2(e0, e1);
+            }
+          } else {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            // the row sum uses the bf16-rounded probabilities the PV product will actually see
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(e[2 * c], e[2 * c + 1]);
-            sum += __low2float(h2) + __high2float(h2);
-            pk[c] = *reinterpret_cast<const uint32_t*>(&h2);
+            for (int c = 0; c < 16; ++c) {
+              float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * c]), kLog2e, -mx_s));
+              float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * c + 1]), kLog2e, -mx_s));
+              e0 = ((vm >> (2 * c)) & 1u) ? e0 : 0.f;
+              e1 = ((vm >> (2 * c + 1)) & 1u) ? e1 : 0.f;
+              sum += e0 + e1;
+              pk[c] = pack_bf16x2(e0, e1);
+            }
           }
         } else {
 #pragma unroll

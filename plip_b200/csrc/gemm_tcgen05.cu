@@ -113,28 +113,12 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, f
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_row_base, uint32_t stage_smem,
                                               uint32_t bias_smem, int row_base, int col_base, int n_blk, int half,
-                                              int lane) {
+                                              int lane, float ln_mean, float ln_rstd) {
   constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   constexpr bool GELU = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD);
   constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || LN_FOLD);
-  float mean = 0.f, rstd = 1.f;
-  if constexpr (LN_FOLD) {
-    // LayerNorm statistics of this thread's row, from the partials the producing GEMM left (fixed order:
-    // bitwise reproducible).  var = E[x^2] - mean^2 in fp32 (TF:371,380 semantics, eps = 1e-5).
-    const int grow = row_base + lane;
-    float s1 = 0.f, s2 = 0.f;
-    if (grow < p.M) {
-      for (int j = 0; j < p.n_partials; ++j) {
-        const float2 t = p.stats_in[static_cast<size_t>(grow) * kStatSlots + j];
-        s1 += t.x;
-        s2 += t.y;
-      }
-    }
-    const float inv_k = 1.0f / static_cast<float>(p.K);
-    mean = s1 * inv_k;
-    rstd = rsqrtf(fmaxf(s2 * inv_k - mean * mean, 0.f) + kLnEps);
-  }
+  float mean = ln_mean, rstd = ln_rstd;
   const uint32_t my_row = stage_smem + lane * 128;
   const int sw = lane & 7;
   const int rb_row = lane >> 3;  // read-back: row within a group of 4
@@ -403,11 +387,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if constexpr (LN_FOLD) {
+        // LayerNorm statistics of this thread's row from the partials the producing GEMM left, summed in a
+        // fixed order (bitwise reproducible); var = E[x^2] - mean^2 in fp32, eps = 1e-5 (TF:371,380).
+        // All slots are fetched at once, before the accumulator wait, so the loads overlap the MMAs.
+        const int grow = row_base + lane;
+        float2 t[kStatSlots];
+#pragma unroll
+        for (int j = 0; j < kStatSlots; ++j)
+          t[j] = (grow < p.M && j < p.n_partials) ? __ldg(p.stats_in + static_cast<size_t>(grow) * kStatSlots + j)
+                                                  : make_float2(0.f, 0.f);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kStatSlots; ++j) {
+          s1 += t[j].x;
+          s2 += t[j].y;
+        }
+        const float inv_k = 1.0f / static_cast<float>(p.K);
+        ln_mean = s1 * inv_k;
+        ln_rstd = rsqrtf(fmaxf(s2 * inv_k - ln_mean * ln_mean, 0.f) + kLnEps);
+      }
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
       epilogue_tile<BN, EPI>(p, trow, epi_base + (warp - 4) * kEpiStageBytes, bias_base + a * BN * 4, row_base,
-                             n_blk * BN, n_blk, half, lane);
+                             n_blk * BN, n_blk, half, lane, ln_mean, ln_rstd);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
