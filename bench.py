@@ -332,6 +332,12 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (tcgen05 GEMM), timed alone -> burst peak
     kr = kernel_rooflines(eng, peaks, torch.cuda.current_stream().cuda_stream)
     dom = max(kr, key=lambda r: r["us"])
+    traffic = None
+    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic = tj[dom["kernel"]]["traffic_mb"] * 1e6
+    except Exception:  # noqa: BLE001
+        traffic = None
     flop_step = PAIRS * (FLOP_IMG + FLOP_TXT) + 2.0 * PAIRS * PAIRS * ws * 512
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
@@ -344,7 +350,7 @@ def run_ours(args):
                    "collective": "all_gather of text embeddings [1024,512] f32 per rank (NCCL)" if ws > 1 else "none"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": dom["tflops"] / peaks["bf16_tflops"], "traffic": None, "kernel": dom["kernel"],
+                     "frac": dom["tflops"] / peaks["bf16_tflops"], "traffic": traffic, "kernel": dom["kernel"],
                      "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
                      "algorithmic_flops_per_launch": 2.0 * dom["M"] * dom["N"] * dom["K"]},
         "cpu_baseline": cpu,
