@@ -207,6 +207,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
+// Pull a 2-D tile into L2 only (no smem destination, no completion signal).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // 2-D tile load, completion on an mbarrier of the executing CTA.
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tm, uint32_t bar,
                                             int32_t c0, int32_t c1) {

@@ -174,6 +174,24 @@ def test_embedder_drop_in(state_dict, golden):
     assert (1 - O.cosine(_t(tout), tref)).max().item() < COS_TOL
 
 
+def test_evaluation_heads(engine):
+    """reproducibility/evaluation: dot + argmax / argsort()[-50:][::-1] on the device == numpy."""
+    from plip_b200.evaluation import ImageRetrieval, ZeroShotClassifier
+    rng = np.random.default_rng(4)
+    img = rng.standard_normal((300, 512)).astype(np.float32)
+    img /= np.linalg.norm(img, axis=1, keepdims=True)
+    txt = img[:120] + 0.05 * rng.standard_normal((120, 512)).astype(np.float32)     # query i matches image i
+    labels = [f"c{i}" for i in range(7)]
+    cls_emb = rng.standard_normal((7, 512)).astype(np.float32)
+    preds = ZeroShotClassifier(engine).predict(img, cls_emb, labels)
+    assert preds == [labels[int(np.argmax(r))] for r in img.dot(cls_emb.T)]          # zero_shot.py:12-13
+    best = ImageRetrieval(engine).best_scores(img, txt)
+    ref = np.stack([t.dot(img.T).argsort()[-50:][::-1] for t in txt])                # retrieval.py:13-16
+    assert np.array_equal(best, ref)
+    train, test = ImageRetrieval(engine).retrieval(img[:120], txt)
+    assert test["p@10"] == 1.0 and train["split"] == "train"
+
+
 def test_full_size_properties(state_dict):
     """BASELINE cfg2 size (batch 1024 bf16): finite, deterministic, consistent with a small-batch run."""
     from plip_b200.engine import Engine
