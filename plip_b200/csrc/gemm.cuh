@@ -16,7 +16,8 @@ enum GemmEpilogue : int {
   // partials of x come from the producing residual GEMM:  out = rstd_r (acc - mean_r colsum_n) + bias'_n.
   EPI_LN_BIAS_BF16 = 5,       // layer_norm1 + q/k/v projection            (TF:371, 310-312)
   EPI_LN_BIAS_GELU_BF16 = 6,  // layer_norm2 + fc1 + QuickGELU             (TF:380, 348-349)
-  EPI_COUNT = 7
+  EPI_NULL = 7,               // (diagnostic) accumulators are read from TMEM and dropped: main-loop-only rate
+  EPI_COUNT = 8
 };
 
 constexpr int kStatSlots = 8;  // per-row partial statistics slots (two per N tile of the producing GEMM: one per epilogue warp half)

@@ -36,16 +36,21 @@ constexpr int kEpiWarps = 8;       // two per TMEM lane quarter, splitting the t
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr uint32_t A_STAGE = BM * BK * 2;
 
-template <int CG, int BN>
+template <int CG, int BN, int EPI = EPI_LN_BIAS_BF16>
 struct Cfg {
   static constexpr int LOAD_N = BN / CG;  // W rows staged by each CTA
   static constexpr uint32_t B_STAGE = LOAD_N * BK * 2;
   static constexpr uint32_t STAGE = A_STAGE + B_STAGE;
-  static constexpr uint32_t EPI_BYTES = kEpiWarps * 32 * 128 + 4 * BN * 4;  // per-warp staging blocks + 2 bias + 2 colsum tiles
-  static constexpr int kMaxStages = (227 * 1024 - 1024 - 512 - EPI_BYTES) / STAGE;
+  static constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
+  // per-warp staging blocks + double-buffered bias tile (+ double-buffered colsum tile for the LN fold)
+  static constexpr uint32_t EPI_BYTES = kEpiWarps * 32 * 128 + (LN_FOLD ? 4 : 2) * BN * 4;
+  static constexpr uint32_t BAR_BYTES = 256;
+  // The dynamic smem window starts 1024-aligned (checked at kernel entry), so no alignment slack is
+  // reserved: that is what lets the residual epilogues run a 6-deep 32 KB operand ring.
+  static constexpr int kMaxStages = (227 * 1024 - BAR_BYTES - EPI_BYTES) / STAGE;
   static constexpr int STAGES = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE + EPI_BYTES + 1024 + 512;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE + EPI_BYTES + BAR_BYTES;
 };
 
 struct GemmDev {
@@ -119,6 +124,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
   constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD);
   constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || LN_FOLD);
   float mean = ln_mean, rstd = ln_rstd;
+  if constexpr (EPI == EPI_NULL) {
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int blk = half; blk < BN / 32; blk += 2) {
+      uint32_t v[32];
+      tmem_ld32(tmem_row_base + blk * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc ^= v[i];
+    }
+    if (acc == 0x12345678u && p.M < 0) reinterpret_cast<uint32_t*>(p.out)[0] = acc;  // keep the loads alive
+    return;
+  }
   const uint32_t my_row = stage_smem + lane * 128;
   const int sw = lane & 7;
   const int rb_row = lane >> 3;  // read-back: row within a group of 4
@@ -242,11 +260,15 @@ template <int CG, int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmDev p) {
-  using C = Cfg<CG, BN>;
+  using C = Cfg<CG, BN, EPI>;
   constexpr int STAGES = C::STAGES;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_raw_u32 = smem_u32(smem_raw);
-  const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
+  const uint32_t smem_base = smem_raw_u32;
+  if ((smem_raw_u32 & 1023u) != 0) {  // SWIZZLE_128B operand tiles need 1024-byte alignment
+    if (threadIdx.x == 0) printf("plip_b200: dynamic shared memory base 0x%x is not 1024-byte aligned\n", smem_raw_u32);
+    __trap();
+  }
   const uint32_t epi_base = smem_base + STAGES * C::STAGE;   // 1024-aligned: 4 x 4 KB staging blocks
   const uint32_t bias_base = epi_base + kEpiWarps * kEpiStageBytes;  // 2 x BN bias + 2 x BN colsum floats
   const uint32_t bar_base = smem_base + STAGES * C::STAGE + C::EPI_BYTES;
@@ -447,7 +469,7 @@ int num_sms() {
 
 template <int CG, int BN, int EPI>
 int launch_inst(const GemmArgs& g, cudaStream_t stream) {
-  using C = Cfg<CG, BN>;
+  using C = Cfg<CG, BN, EPI>;
   auto kern = gemm_kernel<CG, BN, EPI>;
   static bool configured = false;
   static int max_groups = 0;  // co-resident CTAs (CG == 1) or CTA pairs (CG == 2) for this kernel
@@ -507,6 +529,7 @@ int launch_epi(const GemmArgs& g, cudaStream_t stream) {
     case EPI_F32: return launch_inst<CG, BN, EPI_F32>(g, stream);
     case EPI_LN_BIAS_BF16: return launch_inst<CG, BN, EPI_LN_BIAS_BF16>(g, stream);
     case EPI_LN_BIAS_GELU_BF16: return launch_inst<CG, BN, EPI_LN_BIAS_GELU_BF16>(g, stream);
+    case EPI_NULL: return launch_inst<CG, BN, EPI_NULL>(g, stream);
     default: set_last_error("launch_gemm: bad epilogue %d", g.epi); return -2;
   }
 }
