@@ -58,6 +58,9 @@ struct Cfg {
 
 struct GemmDev {
   int M, N, K;
+  int tma_store;  // bf16 epilogues: write the staged blocks with TMA bulk stores instead of read-back + STG
+  int st_mode;  // PLIP_GEMM_ST: 0 default stores, 1 st.global.cs, 2 L1::no_allocate (experiment)
+  int dbg;  // diagnostic (PLIP_GEMM_DBG): 1 = no global stores, 2 = no staging and no stores, 3 = no math either
   const float* bias;
   void* out;
   int ldo;
@@ -83,6 +86,16 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
+}
+// Streaming (evict-first) 16-byte global store: GEMM outputs are far larger than L2 and must not push the
+// operand tiles other CTAs are about to re-read out of it.
+__device__ __forceinline__ void st_global_cs_v4(void* ptr, uint4 v, int mode) {
+  if (mode == 1)
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  else if (mode == 2)
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  else
+    *reinterpret_cast<uint4*>(ptr) = v;
 }
 __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   float4 v;
@@ -119,7 +132,8 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, f
 
 // One accumulator tile (this warp's 32 rows x BN columns) -> global memory.
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_row_base, uint32_t stage_smem,
+__device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMap* tmC, uint32_t tmem_row_base,
+                                              uint32_t stage_smem,
                                               uint32_t bias_smem, int row_base, int col_base, int n_blk, int half,
                                               int lane, float ln_mean, float ln_rstd) {
   constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
@@ -149,22 +163,43 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
 #pragma unroll 1
     for (int blk = half; blk < BN / 64; blk += 2) {
       // 64 columns -> 128 B of bf16 per row
+      if (p.tma_store) {  // the previous bulk store must have finished reading this staging block
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int half2 = 0; half2 < 2; ++half2) {
         float f[32];
-        load_acc32<HAS_BIAS, LN_FOLD, BN>(tmem_row_base + blk * 64 + half * 32, bias_smem + (blk * 64 + half * 32) * 4,
+        load_acc32<HAS_BIAS, LN_FOLD, BN>(tmem_row_base + blk * 64 + half2 * 32, bias_smem + (blk * 64 + half2 * 32) * 4,
                                           mean, rstd, f);
+        if (p.dbg >= 2) {
+          float a = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a += f[i];
+          if (a == 1.2345e30f) reinterpret_cast<float*>(p.out)[0] = a;
+          continue;
+        }
         if constexpr (GELU) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int chunk = half * 4 + c;
+          const int chunk = half2 * 4 + c;
           st_shared_v4(my_row + ((chunk ^ sw) << 4), pack_bf16x2(f[8 * c + 0], f[8 * c + 1]),
                        pack_bf16x2(f[8 * c + 2], f[8 * c + 3]), pack_bf16x2(f[8 * c + 4], f[8 * c + 5]),
                        pack_bf16x2(f[8 * c + 6], f[8 * c + 7]));
         }
+      }
+      if (p.tma_store) {
+        // the staging block is laid out exactly as a SWIZZLE_128B [32 rows x 64 bf16] TMA box
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && p.dbg != 1) {
+          tma_store_2d(tmC, stage_smem, col_base + blk * 64, row_base);
+          tma_store_commit();
+        }
+        continue;
       }
       __syncwarp();
       __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
@@ -173,11 +208,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
         const int r = i * 4 + rb_row;
         const uint4 v = ld_shared_v4(stage_smem + r * 128 + ((rb_chunk ^ (r & 7)) << 4));
         const int grow = row_base + r;
-        if (grow < p.M)
-          *reinterpret_cast<uint4*>(out + static_cast<size_t>(grow) * p.ldo + col_base + blk * 64 + rb_chunk * 8) = v;
+        if (grow < p.M && p.dbg != 1)
+          st_global_cs_v4(out + static_cast<size_t>(grow) * p.ldo + col_base + blk * 64 + rb_chunk * 8, v, p.st_mode);
       }
       __syncwarp();
     }
+    if (p.tma_store && lane == 0) tma_store_wait_read();  // staging is reused by the next tile right away
+    __syncwarp();
   } else {
     // per-row (sum, sum of squares) of the updated residual rows this lane writes (rows i*4 + rb_row)
     float st1[8], st2[8];
@@ -262,7 +299,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, uint32_t tmem_ro
 template <int CG, int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const GemmDev p) {
+            const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
   using C = Cfg<CG, BN, EPI>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -436,7 +473,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      epilogue_tile<BN, EPI>(p, trow, epi_base + warp * kEpiStageBytes, bias_base + a * BN * 4, row_base,
+      epilogue_tile<BN, EPI>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + a * BN * 4, row_base,
                              n_blk * BN, n_blk, half, lane, ln_mean, ln_rstd);
       tc_fence_before();
       __syncwarp();
@@ -447,6 +484,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       a ^= 1;
       if (a == 0) aph ^= 1u;
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -505,9 +543,21 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_bf16_2d(&tmA, g.A, g.M, g.K, (uint64_t)g.lda * 2, BM, BK)) return rc;
   if (int rc = make_tmap_bf16_2d(&tmB, g.W, g.N, g.K, (uint64_t)g.ldw * 2, C::LOAD_N, BK)) return rc;
+  constexpr bool kOutBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_BF16 ||
+                             EPI == EPI_LN_BIAS_GELU_BF16);
+  static const int env_tma_store = env_int("PLIP_GEMM_TMA_STORE", 0);
+  const bool tma_store = kOutBf16 && env_tma_store != 0;
+  CUtensorMap tmC = tmA;  // placeholder when unused
+  if (tma_store)
+    if (int rc = make_tmap_bf16_2d(&tmC, g.out, g.M, g.N, (uint64_t)g.ldo * 2, 32, 64)) return rc;
 
   GemmDev p;
   p.M = g.M; p.N = g.N; p.K = g.K;
+  static const int env_dbg = env_int("PLIP_GEMM_DBG", 0);
+  p.dbg = env_dbg;
+  static const int env_st = env_int("PLIP_GEMM_ST", 0);
+  p.st_mode = env_st;
+  p.tma_store = tma_store ? 1 : 0;
   p.bias = g.bias; p.out = g.out; p.ldo = g.ldo; p.pos = g.pos;
   p.colsum = g.colsum; p.stats_in = g.stats_in; p.n_partials = g.n_partials;
   p.xb_out = g.xb_out; p.stats_out = g.stats_out;
@@ -517,7 +567,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   int groups = max_groups;
   if (groups > num_tiles) groups = num_tiles;
 
-  PLIP_CUDA_CHECK(launch_pdl(kern, dim3(groups * CG), dim3(kThreads), C::SMEM_BYTES, stream, CG, tmA, tmB, p));
+  PLIP_CUDA_CHECK(launch_pdl(kern, dim3(groups * CG), dim3(kThreads), C::SMEM_BYTES, stream, CG, tmA, tmB, tmC, p));
   ++g_launch_count;
   return 0;
 }

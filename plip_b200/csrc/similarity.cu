@@ -167,6 +167,182 @@ similarity_topk_kernel(const float* __restrict__ Q, int64_t n, const float* __re
   }
 }
 
+// ---- fused similarity + top-k, GEMM-shaped: 64 queries x a slice of the space per CTA ---------------
+// The score tile is produced exactly like similarity_kernel (fp32 FMA, norms folded in) but stays in
+// shared memory; each warp then folds 8 rows into per-row sorted top-k lists (also in smem).  Candidates
+// below the current k-th best are rejected with one compare, so insertions are rare after warm-up.
+// The space is split over gridDim.y CTAs per query tile; the last CTA to finish merges the partial lists
+// (threadfence + atomic ticket).  Ordering: higher score first, ties by lower index (deterministic).
+constexpr int kTkThreads = 256;
+constexpr int kTkSmemFloats = 2 * TK * (TM + 4) + TM + TN + TM * (TN + 1) + TM * kTopkMax;  // + int lists
+
+struct TopkLists {
+  float* v;  // [TM][kTopkMax]
+  int* i;    // [TM][kTopkMax]
+};
+
+// Insert (s, id) into the sorted list of `row` (one warp, k <= 64: lane holds entries lane and lane + 32).
+__device__ __forceinline__ void topk_insert(const TopkLists& L, int row, int k, float s, int id, int lane) {
+  float* lv = L.v + row * kTopkMax;
+  int* li = L.i + row * kTopkMax;
+  const float v0 = lane < k ? lv[lane] : -INFINITY, v1 = lane + 32 < k ? lv[lane + 32] : -INFINITY;
+  const int i0 = lane < k ? li[lane] : 0x7fffffff, i1 = lane + 32 < k ? li[lane + 32] : 0x7fffffff;
+  const unsigned b0 = __ballot_sync(0xffffffffu, lane < k && better(v0, i0, s, id));
+  const unsigned b1 = __ballot_sync(0xffffffffu, lane + 32 < k && better(v1, i1, s, id));
+  const int pos = __popc(b0) + __popc(b1);  // entries that stay ahead of the candidate
+  if (pos >= k) return;
+  __syncwarp();
+  if (lane >= pos && lane + 1 < k) { lv[lane + 1] = v0; li[lane + 1] = i0; }
+  if (lane + 32 >= pos && lane + 33 < k) { lv[lane + 33] = v1; li[lane + 33] = i1; }
+  __syncwarp();
+  if (lane == 0) { lv[pos] = s; li[pos] = id; }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kTkThreads)
+similarity_topk_tiled_kernel(const float* __restrict__ Q, int64_t n, const float* __restrict__ Sp, int64_t m, int K,
+                             float scale, int norm_q, int norm_s, int k, int tiles_per_split,
+                             float* __restrict__ scratch_v, int* __restrict__ scratch_i,
+                             unsigned* __restrict__ tickets, int32_t* __restrict__ idx, float* __restrict__ val) {
+  extern __shared__ float tk_smem[];
+  float (*As)[TM + 4] = reinterpret_cast<float (*)[TM + 4]>(tk_smem);
+  float (*Bs)[TN + 4] = reinterpret_cast<float (*)[TN + 4]>(tk_smem + TK * (TM + 4));
+  float* inv_a = tk_smem + 2 * TK * (TM + 4);
+  float* inv_b = inv_a + TM;
+  float (*Sc)[TN + 1] = reinterpret_cast<float (*)[TN + 1]>(inv_b + TN);
+  TopkLists L;
+  L.v = inv_b + TN + TM * (TN + 1);
+  L.i = reinterpret_cast<int*>(L.v + TM * kTopkMax);
+  __shared__ unsigned last_flag;
+
+  pdl_wait();
+  pdl_launch_dependents();
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * TM;
+  const int lr = t >> 2, lk = (t & 3) * 4, ty = t >> 4, tx = t & 15;
+  const int64_t total_tiles = (m + TN - 1) / TN;
+  const int64_t tile_lo = (int64_t)blockIdx.y * tiles_per_split;
+  const int64_t tile_hi = min(total_tiles, tile_lo + tiles_per_split);
+
+  for (int j = t; j < TM * kTopkMax; j += kTkThreads) { L.v[j] = -INFINITY; L.i[j] = 0x7fffffff; }
+  const bool a_ok = row0 + lr < n;
+  const float* ap = Q + (row0 + lr) * K + lk;
+  bool have_inv_a = false;
+
+  for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
+    const int64_t col0 = tile * TN;
+    const bool b_ok = col0 + lr < m;
+    const float* bp = Sp + (col0 + lr) * K + lk;
+    float acc[4][4] = {};
+    float ssa = 0.f, ssb = 0.f;
+    for (int k0 = 0; k0 < K; k0 += TK) {
+      const float4 av = a_ok ? __ldg(reinterpret_cast<const float4*>(ap + k0)) : make_float4(0, 0, 0, 0);
+      const float4 bv = b_ok ? __ldg(reinterpret_cast<const float4*>(bp + k0)) : make_float4(0, 0, 0, 0);
+      ssa += av.x * av.x + av.y * av.y + av.z * av.z + av.w * av.w;
+      ssb += bv.x * bv.x + bv.y * bv.y + bv.z * bv.z + bv.w * bv.w;
+      __syncthreads();
+      As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
+      Bs[lk + 0][lr] = bv.x; Bs[lk + 1][lr] = bv.y; Bs[lk + 2][lr] = bv.z; Bs[lk + 3][lr] = bv.w;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < TK; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float ar[4] = {a.x, a.y, a.z, a.w};
+        const float br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+    }
+    ssa += __shfl_xor_sync(0xffffffffu, ssa, 1);
+    ssa += __shfl_xor_sync(0xffffffffu, ssa, 2);
+    ssb += __shfl_xor_sync(0xffffffffu, ssb, 1);
+    ssb += __shfl_xor_sync(0xffffffffu, ssb, 2);
+    if ((t & 3) == 0) {
+      if (!have_inv_a) inv_a[lr] = norm_q ? 1.0f / sqrtf(ssa) : 1.0f;
+      inv_b[lr] = norm_s ? 1.0f / sqrtf(ssb) : 1.0f;
+    }
+    have_inv_a = true;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = (row0 + ty * 4 + i < n) && (col0 + tx * 4 + j < m);
+        Sc[ty * 4 + i][tx * 4 + j] = ok ? acc[i][j] * scale * inv_a[ty * 4 + i] * inv_b[tx * 4 + j] : -INFINITY;
+      }
+    __syncthreads();
+    // fold the tile into the per-row lists: warp w owns rows 8w .. 8w+7
+    for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        const float s = Sc[r][lane + 32 * hb];
+        const int id = (int)(col0 + lane + 32 * hb);
+        const float thr = L.v[r * kTopkMax + k - 1];
+        const int thr_i = L.i[r * kTopkMax + k - 1];
+        unsigned pass = __ballot_sync(0xffffffffu, s > -INFINITY && better(s, id, thr, thr_i));
+        while (pass) {
+          const int b = __ffs(pass) - 1;
+          pass &= pass - 1;
+          topk_insert(L, r, k, __shfl_sync(0xffffffffu, s, b), __shfl_sync(0xffffffffu, id, b), lane);
+        }
+      }
+    }
+    // (the next tile's first __syncthreads orders these list updates before Sc is overwritten)
+  }
+  __syncthreads();
+
+  const int splits = gridDim.y;
+  if (splits == 1) {
+    for (int j = t; j < TM * k; j += kTkThreads) {
+      const int r = j / k, c = j - r * k;
+      if (row0 + r < n) {
+        const int id = L.i[r * kTopkMax + c];
+        idx[(row0 + r) * k + c] = id == 0x7fffffff ? -1 : id;
+        if (val) val[(row0 + r) * k + c] = L.v[r * kTopkMax + c];
+      }
+    }
+    return;
+  }
+  // publish the partial lists, take a ticket; the last CTA of this query tile merges them
+  for (int j = t; j < TM * k; j += kTkThreads) {
+    const int r = j / k, c = j - r * k;
+    const int64_t o = (((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * TM + r) * k + c;
+    scratch_v[o] = L.v[r * kTopkMax + c];
+    scratch_i[o] = L.i[r * kTopkMax + c];
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last_flag = (atomicAdd(&tickets[blockIdx.x], 1u) == (unsigned)(splits - 1)) ? 1u : 0u;
+  __syncthreads();
+  if (!last_flag) return;
+  __threadfence();
+  for (int sp = 0; sp < splits; ++sp) {
+    if (sp == (int)blockIdx.y) continue;  // our own partial lists are already in smem
+    for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+      const int64_t o = (((int64_t)sp * gridDim.x + blockIdx.x) * TM + r) * k;
+      for (int c = 0; c < k; ++c) {
+        const float s = __ldcg(scratch_v + o + c);
+        const int id = __ldcg(scratch_i + o + c);
+        if (id == 0x7fffffff) break;  // sorted: the rest of this partial list is empty
+        if (!better(s, id, L.v[r * kTopkMax + k - 1], L.i[r * kTopkMax + k - 1])) break;  // sorted: nothing better follows
+        topk_insert(L, r, k, s, id, lane);
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = t; j < TM * k; j += kTkThreads) {
+    const int r = j / k, c = j - r * k;
+    if (row0 + r < n) {
+      const int id = L.i[r * kTopkMax + c];
+      idx[(row0 + r) * k + c] = id == 0x7fffffff ? -1 : id;
+      if (val) val[(row0 + r) * k + c] = L.v[r * kTopkMax + c];
+    }
+  }
+}
+
 }  // namespace
 
 int launch_similarity(const float* a, int64_t n, const float* b, int64_t m, float scale, bool norm_a, bool norm_b,
@@ -189,8 +365,47 @@ int launch_similarity_topk(const float* q, int64_t n, const float* s, int64_t m,
   PLIP_REQUIRE(n > 0 && m > 0, "similarity_topk: empty operand");
   PLIP_REQUIRE(k >= 1 && k <= kTopkMax, "similarity_topk: k=%d out of range [1,%d]", k, kTopkMax);
   PLIP_REQUIRE(n <= 0x7fffffff && m <= 0x7fffffff, "similarity_topk: operand too large");
-  PLIP_CUDA_CHECK(launch_pdl(similarity_topk_kernel, dim3((unsigned)n), dim3(kTopkThreads), 0, st, 1, q, n, s, m,
-                             (int)kProj, scale, norm_q ? 1 : 0, norm_s ? 1 : 0, k, idx, val));
+  if (n * m < (int64_t)1 << 16) {
+    // tiny problems (e.g. a handful of class prompts): one CTA per query streaming the space
+    PLIP_CUDA_CHECK(launch_pdl(similarity_topk_kernel, dim3((unsigned)n), dim3(kTopkThreads), 0, st, 1, q, n, s, m,
+                               (int)kProj, scale, norm_q ? 1 : 0, norm_s ? 1 : 0, k, idx, val));
+    ++g_launch_count;
+    return 0;
+  }
+  static bool configured = false;
+  const size_t smem = (size_t)(kTkSmemFloats + TM * kTopkMax) * 4;
+  if (!configured) {
+    PLIP_CUDA_CHECK(cudaFuncSetAttribute(similarity_topk_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+    configured = true;
+  }
+  const int64_t row_tiles = (n + TM - 1) / TM, space_tiles = (m + TN - 1) / TN;
+  PLIP_REQUIRE(row_tiles <= 0x7fffffff, "similarity_topk: too many queries");
+  int64_t splits = (2 * 148 + row_tiles - 1) / row_tiles;  // aim at ~2 CTAs per SM
+  if (splits > space_tiles) splits = space_tiles;
+  if (splits > 64) splits = 64;
+  if (splits < 1) splits = 1;
+  const int tiles_per_split = (int)((space_tiles + splits - 1) / splits);
+  splits = (space_tiles + tiles_per_split - 1) / tiles_per_split;
+  float* scratch_v = nullptr;
+  int* scratch_i = nullptr;
+  unsigned* tickets = nullptr;
+  void* scratch = nullptr;
+  if (splits > 1) {
+    const size_t ent = (size_t)splits * row_tiles * TM * k;
+    const size_t bytes = ent * 8 + (size_t)row_tiles * 4;
+    PLIP_CUDA_CHECK(cudaMallocAsync(&scratch, bytes, st));
+    scratch_v = static_cast<float*>(scratch);
+    scratch_i = reinterpret_cast<int*>(scratch_v + ent);
+    tickets = reinterpret_cast<unsigned*>(scratch_i + ent);
+    PLIP_CUDA_CHECK(cudaMemsetAsync(tickets, 0, (size_t)row_tiles * 4, st));
+  }
+  dim3 grid((unsigned)row_tiles, (unsigned)splits);
+  cudaError_t le = launch_pdl(similarity_topk_tiled_kernel, grid, dim3(kTkThreads), smem, st, 1, q, n, s, m, (int)kProj,
+                              scale, norm_q ? 1 : 0, norm_s ? 1 : 0, k, tiles_per_split, scratch_v, scratch_i, tickets,
+                              idx, val);
+  if (scratch) cudaFreeAsync(scratch, st);
+  PLIP_CUDA_CHECK(le);
   ++g_launch_count;
   return 0;
 }

@@ -218,3 +218,26 @@ def test_similarity_and_topk(L):
     y = x.clone()
     _check(L.plip_l2_normalize(y.data_ptr(), 33, 512, _stream()), "l2")
     assert (y - x / x.norm(dim=-1, keepdim=True)).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("n,m,k", [(200, 3000, 50), (1000, 777, 10), (3, 40000, 64), (130, 64, 1)])
+def test_similarity_topk_tiled(L, n, m, k):
+    """GEMM-shaped fused top-k (never materialises [n,m]) == torch.topk of the full fp32 score matrix."""
+    dev = "cuda"
+    g = torch.Generator().manual_seed(n + m + k)
+    a = torch.randn(n, 512, generator=g).to(dev)
+    b = torch.randn(m, 512, generator=g).to(dev)
+    idx = torch.empty(n, k, device=dev, dtype=torch.int32)
+    val = torch.empty(n, k, device=dev)
+    _check(L.plip_similarity_topk(a.data_ptr(), n, b.data_ptr(), m, C.c_float(10.0), 1, 1, k, idx.data_ptr(),
+                                  val.data_ptr(), _stream()), "topk")
+    an = a.double() / a.double().norm(dim=-1, keepdim=True)
+    bn = b.double() / b.double().norm(dim=-1, keepdim=True)
+    ref = (10.0 * an @ bn.t())
+    rv, ri = ref.topk(k, dim=-1)
+    assert (rv.float() - val).abs().max().item() < 1e-4
+    # indices must agree except where two scores tie within fp32 rounding
+    mism = ri.int() != idx
+    if mism.any():
+        picked = ref.gather(1, idx.long())
+        assert (picked - rv).abs()[mism].max().item() < 1e-5
