@@ -545,7 +545,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   if (int rc = make_tmap_bf16_2d(&tmB, g.W, g.N, g.K, (uint64_t)g.ldw * 2, C::LOAD_N, BK)) return rc;
   constexpr bool kOutBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_BF16 ||
                              EPI == EPI_LN_BIAS_GELU_BF16);
-  static const int env_tma_store = env_int("PLIP_GEMM_TMA_STORE", 0);
+  static const int env_tma_store = env_int("PLIP_GEMM_TMA_STORE", 1);  // 0 = read-back + STG.128 path
   const bool tma_store = kOutBf16 && env_tma_store != 0;
   CUtensorMap tmC = tmA;  // placeholder when unused
   if (tma_store)
