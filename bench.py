@@ -219,6 +219,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
+    torch.set_num_threads(max(1, usable_cores() // max(1, ws)))   # ranks share the host cores while packing weights
     peaks = _peaks()
 
     cpu = None
