@@ -3,13 +3,15 @@
 // The forward pass of one micro-batch is a fixed sequence of stream-ordered kernel launches:
 //   vision (TF:modeling_clip.py:667-691, 829-863)
 //     im2col(+u8 normalise) -> patch GEMM (+pos emb, scatter past the class row) -> class rows -> pre-LN
-//     12 x [ LN1 -> QKV GEMM(+bias) -> fused attention -> out GEMM(+bias +residual)
-//            LN2 -> fc1 GEMM(+bias +QuickGELU) -> fc2 GEMM(+bias +residual) ]
+//     -> bf16 copy + row statistics
+//     12 x [ QKV GEMM (LN1 folded, +bias) -> fused attention -> out GEMM (+bias +residual, emits bf16 copy + stats)
+//            fc1 GEMM (LN2 folded, +bias +QuickGELU) -> fc2 GEMM (+bias +residual, emits bf16 copy + stats) ]
 //     CLS-row post-LN -> projection GEMM [-> L2 normalise]
 //   text (TF:531-589, 793-825): token+pos gather & EOS search -> same 12 layers (causal/padding mask)
 //     -> EOS-row final-LN -> projection GEMM [-> L2 normalise]
-// Residual stream fp32 (X), GEMM operands bf16 (Xn, QKV, H): cosine >= 1-1e-4 vs the fp32 reference
-// needs the fp32 residual/LN/softmax.  No allocation and no host sync on this path.
+// Residual stream fp32 (X), GEMM operands bf16 (Xn = bf16(X), AO, QKV, H): cosine >= 1-1e-4 vs the fp32
+// reference needs the fp32 residual / LN statistics / softmax.  No allocation and no host sync
+// on this path.
 #include "kernels.cuh"
 
 #include <string.h>

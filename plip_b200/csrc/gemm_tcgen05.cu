@@ -59,7 +59,6 @@ struct Cfg {
 struct GemmDev {
   int M, N, K;
   int tma_store;  // bf16 epilogues: write the staged blocks with TMA bulk stores instead of read-back + STG
-  int st_mode;  // PLIP_GEMM_ST: 0 default stores, 1 st.global.cs, 2 L1::no_allocate (experiment)
   int dbg;  // diagnostic (PLIP_GEMM_DBG): 1 = no global stores, 2 = no staging and no stores, 3 = no math either
   const float* bias;
   void* out;
@@ -86,16 +85,6 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
-}
-// Streaming (evict-first) 16-byte global store: GEMM outputs are far larger than L2 and must not push the
-// operand tiles other CTAs are about to re-read out of it.
-__device__ __forceinline__ void st_global_cs_v4(void* ptr, uint4 v, int mode) {
-  if (mode == 1)
-    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-  else if (mode == 2)
-    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-  else
-    *reinterpret_cast<uint4*>(ptr) = v;
 }
 __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   float4 v;
@@ -209,7 +198,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
         const uint4 v = ld_shared_v4(stage_smem + r * 128 + ((rb_chunk ^ (r & 7)) << 4));
         const int grow = row_base + r;
         if (grow < p.M && p.dbg != 1)
-          st_global_cs_v4(out + static_cast<size_t>(grow) * p.ldo + col_base + blk * 64 + rb_chunk * 8, v, p.st_mode);
+          *reinterpret_cast<uint4*>(out + static_cast<size_t>(grow) * p.ldo + col_base + blk * 64 + rb_chunk * 8) = v;
       }
       __syncwarp();
     }
@@ -555,8 +544,6 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   p.M = g.M; p.N = g.N; p.K = g.K;
   static const int env_dbg = env_int("PLIP_GEMM_DBG", 0);
   p.dbg = env_dbg;
-  static const int env_st = env_int("PLIP_GEMM_ST", 0);
-  p.st_mode = env_st;
   p.tma_store = tma_store ? 1 : 0;
   p.bias = g.bias; p.out = g.out; p.ldo = g.ldo; p.pos = g.pos;
   p.colsum = g.colsum; p.stats_in = g.stats_in; p.n_partials = g.n_partials;

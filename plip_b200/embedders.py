@@ -61,7 +61,7 @@ class CLIPEmbedder(AbstractEmbedder):
         outs: List[torch.Tensor] = []
         eng = getattr(self.model, "engine", None)
         for chunk in chunks(list(list_of_images), max(int(batch_size), 256)):
-            tiles = to_uint8_tiles(chunk)
+            tiles = to_uint8_tiles(chunk, int(num_workers))
             if eng is not None:
                 outs.append(eng.encode_images_host(tiles, normalize=True))
             else:  # any OpenAI-clip-like model

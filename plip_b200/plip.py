@@ -27,12 +27,13 @@ from .preprocess import chunks, to_uint8_tiles
 class PLIP:
 
     def __init__(self, model_name, auth_token=None, *, model: Optional[PlipCLIPModel] = None, preprocess=None,
-                 max_micro_batch: int = 1024):
+                 max_micro_batch: int = 1024, num_workers: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("plip_b200.PLIP needs a CUDA device; there is no CPU fallback")
         self.device = "cuda"
         self.model_name = model_name
         self.max_micro_batch = max_micro_batch
+        self.num_workers = int(num_workers)      # host threads for image decode / resize (0 = in-line)
         if model is not None:
             self.model, self.preprocess, self.model_hash = model, preprocess, hash
         else:
@@ -79,7 +80,7 @@ class PLIP:
             pending, n_pending = [], 0
 
         for chunk in chunks(images, int(batch_size)):
-            pending.append(to_uint8_tiles(chunk))
+            pending.append(to_uint8_tiles(chunk, self.num_workers))
             n_pending += len(chunk)
             if n_pending >= flush:
                 _flush()

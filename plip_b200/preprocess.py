@@ -43,11 +43,24 @@ def resize_center_crop(img: PIL.Image.Image, size: int = SIZE) -> PIL.Image.Imag
     return img.crop((left, top, left + size, top + size))
 
 
-def to_uint8_tiles(images: Sequence[ImageLike]) -> np.ndarray:
-    """Batch of images -> contiguous uint8 array ``[n,224,224,3]`` (NHWC)."""
+def _one_tile(im: ImageLike) -> np.ndarray:
+    return np.asarray(resize_center_crop(load_rgb(im)))
+
+
+def to_uint8_tiles(images: Sequence[ImageLike], workers: int = 0) -> np.ndarray:
+    """Batch of images -> contiguous uint8 array ``[n,224,224,3]`` (NHWC).
+
+    ``workers > 1`` decodes / resizes in a thread pool (PIL releases the GIL in its C loops) — the host-side
+    counterpart of the reference's ``DataLoader(num_workers=…)`` (``embedders/plip.py:39``)."""
     out = np.empty((len(images), SIZE, SIZE, 3), dtype=np.uint8)
+    if workers > 1 and len(images) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            for i, tile in enumerate(ex.map(_one_tile, images)):
+                out[i] = tile
+        return out
     for i, im in enumerate(images):
-        out[i] = np.asarray(resize_center_crop(load_rgb(im)))
+        out[i] = _one_tile(im)
     return out
 
 

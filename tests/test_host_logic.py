@@ -46,6 +46,7 @@ def test_preprocess_identity_on_224_tiles():
     out = P.to_uint8_tiles([PIL.Image.fromarray(t) for t in tiles])
     assert out.dtype == np.uint8 and np.array_equal(out, tiles)
     assert np.array_equal(P.to_uint8_tiles(list(tiles)), tiles)   # arrays accepted too
+    assert np.array_equal(P.to_uint8_tiles(list(tiles), workers=3), tiles)   # threaded decode keeps the order
     gray = PIL.Image.fromarray(tiles[0, :, :, 0])
     assert P.to_uint8_tiles([gray]).shape == (1, 224, 224, 3)     # convert_rgb
 
