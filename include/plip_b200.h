@@ -105,6 +105,14 @@ PLIP_API int plip_encode_text(plip_engine_t* e, const void* ids_dev, int ids_dty
                               const void* attention_mask_dev, int64_t n, int seq_len, float* out_dev,
                               int normalize, void* stream);
 
+/* Same, processing only the first prefix_len (<= seq_len) positions of every row.  The pooled output of a
+ * caption depends only on positions up to its first eos (causal attention, TF:546-557,571-584), so with
+ * prefix_len >= (longest first-eos position + 1) the result equals plip_encode_text at prefix_len/seq_len of
+ * the work — what typical prompts ("An H&E image patch of ...", ~12 of 77 tokens) need. */
+PLIP_API int plip_encode_text_prefix(plip_engine_t* e, const void* ids_dev, int ids_dtype,
+                                     const void* attention_mask_dev, int64_t n, int seq_len, int prefix_len,
+                                     float* out_dev, int normalize, void* stream);
+
 /* Similarity head: logits_per_image[n,m] = scale * norm(img)[n,512] . norm(txt)[m,512]^T
  * (TF:923-930; numpy versions at plip.py:73-76, evaluation/zero_shot/zero_shot.py:12,
  * evaluation/retrieval/retrieval.py:14).  normalize_img / normalize_txt select which side is
@@ -127,7 +135,8 @@ PLIP_API int plip_l2_normalize(float* x_dev, int64_t n, int dim, void* stream);
 /* ---- host-buffer convenience (end-to-end path; copies are inside the call) ------------------- */
 /* pixels_host / ids_host / out_host are host pointers (pinned or pageable).  The call stages
  * micro-batches through pinned buffers on two streams (H2D overlapped with compute), writes the
- * float32 [n,512] result to out_host and returns after the last D2H completed. */
+ * float32 [n,512] result to out_host and returns after the last D2H completed.
+ * plip_encode_text_host scans the ids for the longest caption and uses plip_encode_text_prefix. */
 PLIP_API int plip_encode_images_host(plip_engine_t* e, const void* pixels_host, int pixel_format, int64_t n,
                                      float* out_host, int normalize);
 PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int ids_dtype,

@@ -48,6 +48,7 @@ SIGNATURES = {
     "plip_max_micro_batch": (_i, [_vp]),
     "plip_encode_images": (_i, [_vp, _vp, _i, _i64, _fp, _i, _vp]),
     "plip_encode_text": (_i, [_vp, _vp, _i, _vp, _i64, _i, _fp, _i, _vp]),
+    "plip_encode_text_prefix": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _fp, _i, _vp]),
     "plip_similarity": (_i, [_fp, _i64, _fp, _i64, _f, _i, _i, _fp, _i64, _vp]),
     "plip_similarity_topk": (_i, [_fp, _i64, _fp, _i64, _f, _i, _i, _i, _vp, _fp, _vp]),
     "plip_l2_normalize": (_i, [_fp, _i64, _i, _vp]),

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kEwThreads) rowstats_cast_kernel(const float* 
 // ------------------------------------------------------------------------------------------------
 template <typename IdT>
 __global__ void __launch_bounds__(kEwThreads) text_embed_kernel(const IdT* __restrict__ ids, int64_t n,
-                                                                int seq_len,
+                                                                int seq_len, int ids_stride,
                                                                 const float* __restrict__ tok,
                                                                 const float* __restrict__ pos,
                                                                 float* __restrict__ x) {
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kEwThreads) text_embed_kernel(const IdT* __res
   const int64_t rows = n * seq_len;
   for (int64_t r = warp; r < rows; r += nwarps) {
     const int t = (int)(r % seq_len);
-    long long id = (long long)ids[r];
+    long long id = (long long)ids[(r / seq_len) * ids_stride + t];  // rows may be a prefix of longer id rows
     id = id < 0 ? 0 : (id >= kVocab ? kVocab - 1 : id);
     const float4* e = reinterpret_cast<const float4*>(tok + id * kTxtDim);
     const float4* p = reinterpret_cast<const float4*>(pos + (int64_t)t * kTxtDim);
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kEwThreads) text_embed_kernel(const IdT* __res
 // (input_ids == eos_token_id).int().argmax(-1) (TF:571-584).  One warp per caption.
 template <typename IdT>
 __global__ void __launch_bounds__(kEwThreads) eos_row_kernel(const IdT* __restrict__ ids, int64_t n,
-                                                             int seq_len, int eos_id,
+                                                             int seq_len, int ids_stride, int eos_id,
                                                              int32_t* __restrict__ row_index) {
   pdl_wait();
   pdl_launch_dependents();
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kEwThreads) eos_row_kernel(const IdT* __restri
     int first = seq_len;
     for (int t0 = 0; t0 < seq_len && first == seq_len; t0 += 32) {
       const int t = t0 + lane;
-      const bool hit = t < seq_len && (long long)ids[b * seq_len + t] == (long long)eos_id;
+      const bool hit = t < seq_len && (long long)ids[b * ids_stride + t] == (long long)eos_id;
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (m) first = t0 + __ffs(m) - 1;
     }
@@ -228,12 +228,13 @@ __global__ void __launch_bounds__(kEwThreads) eos_row_kernel(const IdT* __restri
 // Key-padding mask -> int32 (1 = attend, 0 = padded key).
 template <typename IdT>
 __global__ void __launch_bounds__(kEwThreads) mask_to_i32_kernel(const IdT* __restrict__ m, int64_t count,
+                                                                 int seq_len, int stride,
                                                                  int32_t* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
        i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = m[i] != 0 ? 1 : 0;
+    out[i] = m[(i / seq_len) * stride + (i % seq_len)] != 0 ? 1 : 0;
 }
 
 // Class-token rows: x[b*50] = class_embedding + position_embedding[0]   (TF:212-217).
@@ -331,18 +332,19 @@ int launch_rowstats_cast(const float* x, int64_t rows, int dim, __nv_bfloat16* x
   return 0;
 }
 
-int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, const float* tok, const float* pos,
-                      float* x, int32_t* eos_rows, int eos_id, cudaStream_t st) {
+int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, int ids_stride, const float* tok,
+                      const float* pos, float* x, int32_t* eos_rows, int eos_id, cudaStream_t st) {
+  PLIP_REQUIRE(ids_stride >= seq_len, "text_embed: ids row stride %d < seq_len %d", ids_stride, seq_len);
   PLIP_REQUIRE(n > 0 && seq_len > 0 && seq_len <= kTxtSeq, "text_embed: bad shape n=%lld seq_len=%d",
                (long long)n, seq_len);
   const int grid = grid_for(n * seq_len, kEwThreads / 32);
   const int grid2 = grid_for(n, kEwThreads / 32);
   if (ids_dtype == PLIP_IDS_I64) {
-    PLIP_CUDA_CHECK(launch_pdl(text_embed_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, tok, pos, x));
-    PLIP_CUDA_CHECK(launch_pdl(eos_row_kernel<long long>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, eos_id, eos_rows));
+    PLIP_CUDA_CHECK(launch_pdl(text_embed_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, ids_stride, tok, pos, x));
+    PLIP_CUDA_CHECK(launch_pdl(eos_row_kernel<long long>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, ids_stride, eos_id, eos_rows));
   } else if (ids_dtype == PLIP_IDS_I32) {
-    PLIP_CUDA_CHECK(launch_pdl(text_embed_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, tok, pos, x));
-    PLIP_CUDA_CHECK(launch_pdl(eos_row_kernel<int>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, eos_id, eos_rows));
+    PLIP_CUDA_CHECK(launch_pdl(text_embed_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, ids_stride, tok, pos, x));
+    PLIP_CUDA_CHECK(launch_pdl(eos_row_kernel<int>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, ids_stride, eos_id, eos_rows));
   } else {
     set_last_error("text_embed: unknown ids dtype %d", ids_dtype);
     return -2;
@@ -352,12 +354,13 @@ int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, co
   return 0;
 }
 
-int launch_mask_to_i32(const void* mask, int dtype, int64_t count, int32_t* out, cudaStream_t st) {
+int launch_mask_to_i32(const void* mask, int dtype, int64_t count, int seq_len, int stride, int32_t* out,
+                       cudaStream_t st) {
   const int grid = grid_for(count, kEwThreads);
   if (dtype == PLIP_IDS_I64)
-    PLIP_CUDA_CHECK(launch_pdl(mask_to_i32_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(mask), count, out));
+    PLIP_CUDA_CHECK(launch_pdl(mask_to_i32_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(mask), count, seq_len, stride, out));
   else
-    PLIP_CUDA_CHECK(launch_pdl(mask_to_i32_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(mask), count, out));
+    PLIP_CUDA_CHECK(launch_pdl(mask_to_i32_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(mask), count, seq_len, stride, out));
   PLIP_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return 0;

@@ -271,20 +271,23 @@ int vision_forward(plip_engine* e, const void* pixels, int fmt, int64_t mb, floa
   return 0;
 }
 
-int text_trunk(plip_engine* e, const void* ids, int ids_dtype, const void* mask, int64_t mb, int S,
+// S = number of leading token positions actually processed (<= stride, the row length of ids / mask).
+// Causality makes rows after a caption's first EOS irrelevant to its pooled output (TF:571-584), so callers
+// that know the longest caption of the batch may pass a shorter S: same result, proportionally less work.
+int text_trunk(plip_engine* e, const void* ids, int ids_dtype, const void* mask, int64_t mb, int S, int stride,
                int num_layers, cudaStream_t st) {
-  if (int rc = launch_text_embed(ids, ids_dtype, mb, S, e->t_tok, e->t_pos, e->X, e->row_idx, kEosId, st)) return rc;
+  if (int rc = launch_text_embed(ids, ids_dtype, mb, S, stride, e->t_tok, e->t_pos, e->X, e->row_idx, kEosId, st)) return rc;
   const int32_t* km = nullptr;
   if (mask) {
-    if (int rc = launch_mask_to_i32(mask, ids_dtype, mb * S, e->kmask, st)) return rc;
+    if (int rc = launch_mask_to_i32(mask, ids_dtype, mb * S, S, stride, e->kmask, st)) return rc;
     km = e->kmask;
   }
   return run_layers(e, e->txt, mb, S, kTxtDim, kTxtFF, kTxtHeads, true, km, num_layers, st);
 }
 
-int text_forward(plip_engine* e, const void* ids, int ids_dtype, const void* mask, int64_t mb, int S, float* out,
-                 int normalize, cudaStream_t st) {
-  if (int rc = text_trunk(e, ids, ids_dtype, mask, mb, S, kLayers, st)) return rc;
+int text_forward(plip_engine* e, const void* ids, int ids_dtype, const void* mask, int64_t mb, int S, int stride,
+                 float* out, int normalize, cudaStream_t st) {
+  if (int rc = text_trunk(e, ids, ids_dtype, mask, mb, S, stride, kLayers, st)) return rc;
   // pooled = final_layer_norm(last_hidden_state)[b, first eos]            TF:modeling_clip.py:562-584
   if (int rc = launch_layernorm(e->X, e->row_idx, kTxtDim, mb, kTxtDim, e->t_fin_g, e->t_fin_b, nullptr,
                                 e->pooled, st)) return rc;
@@ -447,7 +450,16 @@ PLIP_API int plip_encode_images(plip_engine_t* e, const void* pixels_dev, int pi
 
 PLIP_API int plip_encode_text(plip_engine_t* e, const void* ids_dev, int ids_dtype, const void* attention_mask_dev,
                               int64_t n, int seq_len, float* out_dev, int normalize, void* stream) {
+  return plip_encode_text_prefix(e, ids_dev, ids_dtype, attention_mask_dev, n, seq_len, seq_len, out_dev, normalize,
+                                 stream);
+}
+
+PLIP_API int plip_encode_text_prefix(plip_engine_t* e, const void* ids_dev, int ids_dtype,
+                                     const void* attention_mask_dev, int64_t n, int seq_len, int prefix_len,
+                                     float* out_dev, int normalize, void* stream) {
   PLIP_REQUIRE(e && ids_dev && out_dev, "plip_encode_text: null argument");
+  PLIP_REQUIRE(prefix_len >= 1 && prefix_len <= seq_len, "plip_encode_text_prefix: prefix_len %d out of [1,%d]",
+               prefix_len, seq_len);
   PLIP_REQUIRE(n > 0, "plip_encode_text: n must be positive (got %lld)", (long long)n);
   PLIP_REQUIRE(seq_len >= 1 && seq_len <= kTxtSeq,
                "Sequence length must be less than max_position_embeddings (got `sequence length`: %d and "
@@ -459,7 +471,7 @@ PLIP_API int plip_encode_text(plip_engine_t* e, const void* ids_dev, int ids_dty
     const int64_t mb = (n - i < e->max_mb) ? (n - i) : e->max_mb;
     const uint8_t* ids = static_cast<const uint8_t*>(ids_dev) + i * seq_len * isz;
     const uint8_t* mk = attention_mask_dev ? static_cast<const uint8_t*>(attention_mask_dev) + i * seq_len * isz : nullptr;
-    if (int rc = text_forward(e, ids, ids_dtype, mk, mb, seq_len, out_dev + i * kProj, normalize, st)) return rc;
+    if (int rc = text_forward(e, ids, ids_dtype, mk, mb, prefix_len, seq_len, out_dev + i * kProj, normalize, st)) return rc;
   }
   return 0;
 }
@@ -557,7 +569,20 @@ PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int i
   uint8_t* d_mask = attention_mask_host ? d_ids + ib_al : nullptr;
   PLIP_CUDA_CHECK(cudaMemcpyAsync(d_ids, ids_host, ib, cudaMemcpyHostToDevice, e->s_compute));
   if (d_mask) PLIP_CUDA_CHECK(cudaMemcpyAsync(d_mask, attention_mask_host, ib, cudaMemcpyHostToDevice, e->s_compute));
-  if (int rc = plip_encode_text(e, d_ids, ids_dtype, d_mask, n, seq_len, e->d_out, normalize, e->s_compute)) return rc;
+  // Longest caption (first EOS position + 1) scanned on the host: rows after the first EOS cannot influence
+  // the pooled output (causal attention), so only that prefix of every row is processed.
+  int prefix = 1;
+  for (int64_t b = 0; b < n && prefix < seq_len; ++b) {
+    int len = seq_len;
+    for (int t = 0; t < seq_len; ++t) {
+      const long long id = ids_dtype == PLIP_IDS_I64 ? static_cast<const long long*>(ids_host)[b * seq_len + t]
+                                                     : (long long)static_cast<const int*>(ids_host)[b * seq_len + t];
+      if (id == kEosId) { len = t + 1; break; }
+    }
+    if (len > prefix) prefix = len;
+  }
+  if (int rc = plip_encode_text_prefix(e, d_ids, ids_dtype, d_mask, n, seq_len, prefix, e->d_out, normalize,
+                                       e->s_compute)) return rc;
   PLIP_CUDA_CHECK(cudaMemcpyAsync(out_host, e->d_out, (size_t)n * kProj * 4, cudaMemcpyDeviceToHost, e->s_compute));
   PLIP_CUDA_CHECK(cudaStreamSynchronize(e->s_compute));
   return 0;
@@ -612,7 +637,7 @@ PLIP_API int plip_dbg_hidden_states(plip_engine_t* e, int tower, const void* inp
     if (int rc = vision_trunk(e, input_dev, input_format, n, num_layers, st)) return rc;
     bytes = (size_t)n * kVisSeq * kVisDim * 4;
   } else {
-    if (int rc = text_trunk(e, input_dev, input_format, attention_mask_dev, n, kTxtSeq, num_layers, st)) return rc;
+    if (int rc = text_trunk(e, input_dev, input_format, attention_mask_dev, n, kTxtSeq, kTxtSeq, num_layers, st)) return rc;
     bytes = (size_t)n * kTxtSeq * kTxtDim * 4;
   }
   PLIP_CUDA_CHECK(cudaMemcpyAsync(hidden_dev, e->X, bytes, cudaMemcpyDeviceToDevice, st));

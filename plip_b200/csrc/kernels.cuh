@@ -13,9 +13,10 @@ int launch_layernorm(const float* x, const int32_t* row_index, int64_t in_row_st
                      const float* gamma, const float* beta, float* out_f32, __nv_bfloat16* out_bf16,
                      cudaStream_t st);
 int launch_rowstats_cast(const float* x, int64_t rows, int dim, __nv_bfloat16* xb, float2* stats, cudaStream_t st);
-int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, const float* tok, const float* pos,
-                      float* x, int32_t* eos_rows, int eos_id, cudaStream_t st);
-int launch_mask_to_i32(const void* mask, int dtype, int64_t count, int32_t* out, cudaStream_t st);
+int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, int ids_stride, const float* tok,
+                      const float* pos, float* x, int32_t* eos_rows, int eos_id, cudaStream_t st);
+int launch_mask_to_i32(const void* mask, int dtype, int64_t count, int seq_len, int stride, int32_t* out,
+                       cudaStream_t st);
 int launch_cls_rows(const float* cls, const float* pos, int64_t n, float* x, cudaStream_t st);
 int launch_l2_normalize(float* x, int64_t rows, int dim, cudaStream_t st);
 

@@ -118,9 +118,16 @@ class Engine:
 
     @torch.no_grad()
     def encode_text(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
-                    normalize: bool = False) -> torch.Tensor:
-        """``get_text_features``: ids ``[n,<=77]`` int32/int64 (+ optional mask) -> ``[n,512]`` f32 (device)."""
+                    normalize: bool = False, prefix_len: Optional[int] = None) -> torch.Tensor:
+        """``get_text_features``: ids ``[n,<=77]`` int32/int64 (+ optional mask) -> ``[n,512]`` f32 (device).
+
+        ``prefix_len``: process only the first ``prefix_len`` positions of every row.  Exact whenever every
+        caption's first eos lies inside the prefix (causal attention); the host path (``encode_text_host``)
+        finds the longest caption itself, a device caller can pass it to avoid a sync."""
         n, s = _check_ids(input_ids, attention_mask)
+        p_len = s if prefix_len is None else int(prefix_len)
+        if not 1 <= p_len <= s:
+            raise ValueError(f"prefix_len {p_len} out of [1, {s}]")
         if n == 0:
             return torch.empty(0, EMBED_DIM, device=self.device)
         idt = _ids_dtype(input_ids.dtype)
@@ -130,8 +137,9 @@ class Engine:
             mask = self._dev(attention_mask.to(input_ids.dtype))
         out = torch.empty(n, EMBED_DIM, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
-            check(self._L.plip_encode_text(self._h, ids.data_ptr(), idt, mask.data_ptr() if mask is not None else None,
-                                           n, s, out.data_ptr(), int(normalize), self._stream()), "plip_encode_text")
+            check(self._L.plip_encode_text_prefix(self._h, ids.data_ptr(), idt,
+                                                  mask.data_ptr() if mask is not None else None, n, s, p_len,
+                                                  out.data_ptr(), int(normalize), self._stream()), "plip_encode_text")
         return out
 
     @torch.no_grad()

@@ -80,6 +80,26 @@ def test_text_real_padding_mask_and_short_sequences(engine, state_dict):
     assert (1 - O.cosine(out_s, ref_s)).max().item() < COS_TOL
 
 
+def test_text_prefix_processing_is_exact(engine, state_dict):
+    """Short prompts (the common case: ~12 of 77 tokens): only the prefix up to the longest first-eos is
+    processed.  Causality makes that exact; compare with the full-length run and with the oracle."""
+    ids, mask = synth.token_ids(40, seed=21, min_len=5)
+    lens = mask.sum(1)
+    keep = lens <= 20
+    ids, mask = ids[keep][:12], mask[keep][:12]
+    assert ids.shape[0] >= 4
+    longest = int(mask.sum(1).max())
+    full = engine.encode_text(ids.cuda(), mask.cuda()).cpu()
+    pre = engine.encode_text(ids.cuda(), mask.cuda(), prefix_len=longest).cpu()
+    host = engine.encode_text_host(ids, mask)                          # scans the ids, picks the prefix itself
+    ref = O.get_text_features(state_dict, ids, mask)
+    assert (1 - O.cosine(pre, full)).max().item() < 1e-5
+    assert torch.equal(host, pre)
+    assert (1 - O.cosine(pre, ref)).max().item() < COS_TOL
+    with pytest.raises(ValueError):
+        engine.encode_text(ids.cuda(), prefix_len=78)
+
+
 def test_uint8_tiles_and_reference_plip_cfg1(engine, golden):
     """cfg1 through the device u8 path: matches the reference PLIP.encode_images golden."""
     tiles = torch.from_numpy(synth.tiles_u8(32, seed=0))
@@ -131,7 +151,7 @@ def test_microbatching_host_path_and_determinism(engine):
     assert torch.equal(engine.encode_images_host(tiles.pin_memory()), full)
     ids, mask = synth.token_ids(100, seed=9)
     t_full = engine.encode_text(ids.cuda(), mask.cuda()).cpu()
-    assert torch.equal(engine.encode_text_host(ids, mask), t_full)
+    assert (1 - O.cosine(engine.encode_text_host(ids, mask), t_full)).max().item() < 1e-5   # host path = prefix run
     assert engine.encode_images(torch.zeros(0, 3, 224, 224)).shape == (0, 512)
 
 

@@ -188,7 +188,7 @@ def sec_host():
     t0 = eng.encode_text(ids.cuda(), mask.cuda()).cpu()
     t1 = eng.encode_text_host(ids, mask)
     print(json.dumps({"host_vs_dev_pageable": (a - b).abs().max().item(), "host_vs_dev_pinned": (a - c).abs().max().item(),
-                      "text_host_vs_dev": (t0 - t1).abs().max().item()}))
+                      "text_host_vs_dev": (t0 - t1).abs().max().item()}))  # host path processes only the longest-caption prefix
 
 
 def sec_perf():
