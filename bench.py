@@ -194,16 +194,23 @@ def kernel_rooflines(eng, peaks, stream):
                                              st_out.data_ptr() if st_out is not None else None, stream), "gemm")
         for _ in range(3):
             call()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            call()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
+        # Same protocol as the peak it is compared with (MEASURED_PEAKS: cuBLAS "best of 10", burst): best of 6
+        # short bursts of 3 launches, separated by a pause so the 1 kW power cap does not pin the clocks low;
+        # the mean over all bursts is reported next to it.
+        bursts = []
+        for _ in range(6):
+            time.sleep(0.03)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                call()
+            e1.record()
+            torch.cuda.synchronize()
+            bursts.append(e0.elapsed_time(e1) / 3)
+        ms = min(bursts)
         tf = 2.0 * M * N * K / ms / 1e9
         res.append({"kernel": f"gemm_tcgen05[{name}]", "M": M, "N": N, "K": K, "us": ms * 1e3, "tflops": tf,
-                    "frac_of_burst_peak": tf / peaks["bf16_tflops"]})
+                    "frac_of_burst_peak": tf / peaks["bf16_tflops"], "us_mean": sum(bursts) / len(bursts) * 1e3})
         del A, W, out, xb, st_out
     return res
 
