@@ -1,0 +1,2 @@
+export PYTHONPATH=.
+timeout 600 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_r1d.json
