@@ -14,7 +14,9 @@
  *   - *_dev pointers are device pointers owned by the caller; the engine owns packed weights and
  *     its workspace (allocated at plip_create, nothing is allocated on the hot path).
  *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, the device-pointer
- *     entry points never synchronise.  One handle per device; a handle is not re-entrant.
+ *     entry points never synchronise the host.  One handle per device; calls on one handle share a
+ *     workspace and are serialised on the device (each call waits, stream-side, for the previous one);
+ *     a handle must not be used from two host threads at once.
  */
 #ifndef PLIP_B200_H_
 #define PLIP_B200_H_

@@ -131,6 +131,9 @@ struct plip_engine {
   __nv_bfloat16* pooled = nullptr;  // [mb, 768]
   int32_t* row_idx = nullptr;       // [mb] EOS rows
   int32_t* kmask = nullptr;         // [mb*77] key padding mask
+  // last use of the shared workspace through the device-pointer API (any caller stream): the host-buffer
+  // path, which runs on the engine's own streams, waits for it before touching the workspace
+  cudaEvent_t ev_last = nullptr;
   // host-buffer path (lazy)
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -380,6 +383,7 @@ PLIP_API int plip_create(const void* host_blob, uint64_t nbytes, float logit_sca
   e->device = device;
   e->max_mb = max_micro_batch;
   e->logit_scale_exp = logit_scale_exp;
+  PLIP_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));
   const WsLayout w = ws_layout(max_micro_batch);
   uint8_t* ws = nullptr;
   if (cudaMalloc(&e->d_blob, nbytes) != cudaSuccess || cudaMalloc(&ws, w.total) != cudaSuccess) {
@@ -424,6 +428,7 @@ PLIP_API int plip_destroy(plip_engine_t* e) {
   }
   if (e->d_out) cudaFree(e->d_out);
   if (e->d_aux) cudaFree(e->d_aux);
+  if (e->ev_last) cudaEventDestroy(e->ev_last);
   if (e->s_compute) cudaStreamDestroy(e->s_compute);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   delete e;
@@ -439,12 +444,14 @@ PLIP_API int plip_encode_images(plip_engine_t* e, const void* pixels_dev, int pi
   PLIP_REQUIRE(n > 0, "plip_encode_images: n must be positive (got %lld)", (long long)n);
   PLIP_REQUIRE(pixel_format >= 0 && pixel_format <= 2, "plip_encode_images: unknown pixel format %d", pixel_format);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PLIP_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_last, 0));  // calls on different streams share one workspace
   const size_t pb = pixel_bytes(pixel_format);
   for (int64_t i = 0; i < n; i += e->max_mb) {
     const int64_t mb = (n - i < e->max_mb) ? (n - i) : e->max_mb;
     if (int rc = vision_forward(e, static_cast<const uint8_t*>(pixels_dev) + i * pb, pixel_format, mb,
                                 out_dev + i * kProj, normalize, st)) return rc;
   }
+  PLIP_CUDA_CHECK(cudaEventRecord(e->ev_last, st));
   return 0;
 }
 
@@ -466,6 +473,7 @@ PLIP_API int plip_encode_text_prefix(plip_engine_t* e, const void* ids_dev, int 
                "max_position_embeddings: %d)", seq_len, kTxtSeq);  // message mirrors TF:243-247
   PLIP_REQUIRE(ids_dtype == PLIP_IDS_I32 || ids_dtype == PLIP_IDS_I64, "plip_encode_text: unknown ids dtype %d", ids_dtype);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PLIP_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_last, 0));
   const size_t isz = ids_dtype == PLIP_IDS_I64 ? 8 : 4;
   for (int64_t i = 0; i < n; i += e->max_mb) {
     const int64_t mb = (n - i < e->max_mb) ? (n - i) : e->max_mb;
@@ -473,6 +481,7 @@ PLIP_API int plip_encode_text_prefix(plip_engine_t* e, const void* ids_dev, int 
     const uint8_t* mk = attention_mask_dev ? static_cast<const uint8_t*>(attention_mask_dev) + i * seq_len * isz : nullptr;
     if (int rc = text_forward(e, ids, ids_dtype, mk, mb, prefix_len, seq_len, out_dev + i * kProj, normalize, st)) return rc;
   }
+  PLIP_CUDA_CHECK(cudaEventRecord(e->ev_last, st));
   return 0;
 }
 
@@ -511,6 +520,7 @@ PLIP_API int plip_encode_images_host(plip_engine_t* e, const void* pixels_host, 
   PLIP_REQUIRE(pixel_format >= 0 && pixel_format <= 2, "plip_encode_images_host: unknown pixel format %d", pixel_format);
   PLIP_CUDA_CHECK(cudaSetDevice(e->device));
   if (int rc = ensure_host_path(e)) return rc;
+  PLIP_CUDA_CHECK(cudaStreamWaitEvent(e->s_compute, e->ev_last, 0));  // earlier device-API work owns the workspace
   const size_t pb = pixel_bytes(pixel_format);
   const int64_t chunk = e->max_mb;
   const size_t in_bytes = (size_t)(n < chunk ? n : chunk) * pb;
@@ -560,6 +570,7 @@ PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int i
   PLIP_REQUIRE(ids_dtype == PLIP_IDS_I32 || ids_dtype == PLIP_IDS_I64, "plip_encode_text_host: unknown ids dtype %d", ids_dtype);
   PLIP_CUDA_CHECK(cudaSetDevice(e->device));
   if (int rc = ensure_host_path(e)) return rc;
+  PLIP_CUDA_CHECK(cudaStreamWaitEvent(e->s_compute, e->ev_last, 0));
   const size_t isz = ids_dtype == PLIP_IDS_I64 ? 8 : 4;
   const size_t ib = (size_t)n * seq_len * isz;
   const size_t ib_al = (ib + 255) & ~(size_t)255;
@@ -641,6 +652,7 @@ PLIP_API int plip_dbg_hidden_states(plip_engine_t* e, int tower, const void* inp
     bytes = (size_t)n * kTxtSeq * kTxtDim * 4;
   }
   PLIP_CUDA_CHECK(cudaMemcpyAsync(hidden_dev, e->X, bytes, cudaMemcpyDeviceToDevice, st));
+  PLIP_CUDA_CHECK(cudaEventRecord(e->ev_last, st));
   return 0;
 }
 

@@ -155,6 +155,25 @@ def test_microbatching_host_path_and_determinism(engine):
     assert engine.encode_images(torch.zeros(0, 3, 224, 224)).shape == (0, 512)
 
 
+def test_calls_on_different_streams_are_serialised(engine):
+    """One handle = one workspace: back-to-back calls on different streams (and the host path right after a
+    device call) must not corrupt each other."""
+    tiles = torch.from_numpy(synth.tiles_u8(64, seed=11)).cuda()
+    ids = synth.token_ids(64, seed=12)[0].cuda()
+    ref_i = engine.encode_images(tiles).clone()
+    ref_t = engine.encode_text(ids).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            a = engine.encode_images(tiles)
+        with torch.cuda.stream(s2):
+            b = engine.encode_text(ids)
+        c = engine.encode_images_host(tiles.cpu())          # engine's own streams, right behind the two above
+        torch.cuda.synchronize()
+        assert torch.equal(a, ref_i) and torch.equal(b, ref_t) and torch.equal(c, ref_i.cpu())
+
+
 def test_plip_class_drop_in(state_dict, golden):
     """The reference-facing class: same call, same return type/shape/order as plip.PLIP (plip.py:31-53)."""
     from plip_b200.plip import PLIP
