@@ -342,8 +342,34 @@ def run_ours(args):
                    "logits_per_image [1024, 1024*n_gpus] f32 copied back to pinned host memory every step; uploads "
                    "double-buffered on a copy stream"}
 
+    # ---- the two towers alone (BASELINE cfg2: "ViT-B/32 vision tower only, batch 1024 bf16"), rank-local
+    def tower(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(5):
+            fn()
+        eb.record()
+        torch.cuda.synchronize()
+        return ea.elapsed_time(eb) / 5
+
+    ms_v = tower(lambda: eng.encode_images(px[0]))
+    ms_t = tower(lambda: eng.encode_text(ids[0]))
     if rank != 0:
         return 0
+    towers = {
+        "vision_tower_1024_bf16": {"ms": ms_v, "img_per_s": PAIRS / ms_v * 1e3, "tflops": PAIRS * FLOP_IMG / ms_v / 1e9,
+                                   "frac_of_burst_peak": PAIRS * FLOP_IMG / ms_v / 1e9 / peaks["bf16_tflops"],
+                                   "frac_of_sustained_peak": PAIRS * FLOP_IMG / ms_v / 1e9 / peaks["bf16_tflops_sustained"]},
+        "text_tower_1024x77": {"ms": ms_t, "captions_per_s": PAIRS / ms_t * 1e3, "tflops": PAIRS * FLOP_TXT / ms_t / 1e9},
+    }
+    try:  # tensor-pipe activity of the layer GEMMs from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        towers["ncu_tensor_pipe_active_pct"] = {k: v["tensor_active_pct"] for k, v in tj.items() if isinstance(v, dict)}
+    except Exception:  # noqa: BLE001
+        pass
     # ---- roofline of the dominant kernel (tcgen05 GEMM), timed alone -> burst peak
     kr = kernel_rooflines(eng, peaks, torch.cuda.current_stream().cuda_stream)
     # dominant kernel = the tcgen05 GEMM template (84 % of the step, profiles/r1f_launches_bench.csv): its four
@@ -376,7 +402,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "extra": {"step_tflops": flop_step / (ms_per_step / 1e3) / 1e12,
                   "step_frac_of_sustained_peak": flop_step / (ms_per_step / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
-                  "kernels": kr},
+                  "kernels": kr, **towers},
     }
     print(json.dumps(line), flush=True)
     return 0
