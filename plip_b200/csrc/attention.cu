@@ -287,16 +287,15 @@ int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int h
   PLIP_REQUIRE(n_seq > 0 && seq_len > 0 && seq_len <= 128, "attention: bad shape n_seq=%lld seq_len=%d",
                (long long)n_seq, seq_len);
   PLIP_REQUIRE(heads > 0 && heads <= 16, "attention: bad head count %d", heads);
-  static bool configured = false;
+  static unsigned long long configured = 0;
   static int grid_cap = 0;
-  if (!configured) {
+  if (first_use_on_device(configured)) {
     PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kAttSmem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     grid_cap = kAttCtasPerSm * sms;
-    configured = true;
   }
   const int D = heads * kHeadDim;
   const int64_t rows = n_seq * seq_len;

@@ -59,6 +59,17 @@ void set_last_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
+// cudaFuncSetAttribute is per device: returns true the first time it is called for the current device with
+// a given per-kernel mask (a process that drives several GPUs configures each kernel once per GPU).
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 // Encode a 2-D bf16 row-major tensor map with 128-byte swizzle.
 // dims: inner (contiguous) extent `cols`, outer extent `rows`, row stride in bytes.
 // box: box_cols (must be 64 bf16 == 128 B for SWIZZLE_128B) x box_rows (<=256).

@@ -501,9 +501,9 @@ template <int CG, int BN, int EPI>
 int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   using C = Cfg<CG, BN, EPI>;
   auto kern = gemm_kernel<CG, BN, EPI>;
-  static bool configured = false;
+  static unsigned long long configured = 0;
   static int max_groups = 0;  // co-resident CTAs (CG == 1) or CTA pairs (CG == 2) for this kernel
-  if (!configured) {
+  if (first_use_on_device(configured)) {
     PLIP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM_BYTES));
     max_groups = num_sms() / CG;
@@ -527,7 +527,6 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
     if (env_int("PLIP_DEBUG", 0))
       fprintf(stderr, "plip_b200: gemm<cg=%d,bn=%d,epi=%d> stages=%d smem=%u max_groups=%d\n", CG, BN, EPI,
               C::STAGES, C::SMEM_BYTES, max_groups);
-    configured = true;
   }
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_bf16_2d(&tmA, g.A, g.M, g.K, (uint64_t)g.lda * 2, BM, BK)) return rc;

@@ -372,12 +372,11 @@ int launch_similarity_topk(const float* q, int64_t n, const float* s, int64_t m,
     ++g_launch_count;
     return 0;
   }
-  static bool configured = false;
+  static unsigned long long configured = 0;
   const size_t smem = (size_t)(kTkSmemFloats + TM * kTopkMax) * 4;
-  if (!configured) {
+  if (first_use_on_device(configured)) {
     PLIP_CUDA_CHECK(cudaFuncSetAttribute(similarity_topk_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-    configured = true;
   }
   const int64_t row_tiles = (n + TM - 1) / TM, space_tiles = (m + TN - 1) / TN;
   PLIP_REQUIRE(row_tiles <= 0x7fffffff, "similarity_topk: too many queries");
