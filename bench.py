@@ -233,10 +233,10 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline:
         sd, cpu = cpu_baseline_sample()
     else:
-        from oracle import weights
-        sd = weights.make_state_dict(0)
+        from plip_b200 import synthetic
+        sd = synthetic.make_state_dict(0)
 
-    from oracle import synth
+    from plip_b200 import synthetic as synth          # data generation only; the oracle is used by the CPU legs alone
     from plip_b200 import distributed as D
     from plip_b200._lib import lib
     from plip_b200.modeling import PlipCLIPModel

@@ -1,85 +1,4 @@
-"""TEST INFRASTRUCTURE — deterministic synthetic CLIP ViT-B/32 weights (HuggingFace names).
+"""TEST INFRASTRUCTURE — re-export of the seeded synthetic weights (``plip_b200.synthetic``).
 
-Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU baseline may import ``oracle``.
-
-No pretrained PLIP checkpoint is reachable offline (``vinid/plip`` needs the network),
-so parity is measured on seeded random weights with the exact state-dict names / shapes of
-``transformers.CLIPModel(CLIPConfig())`` (listed in SURVEY.md §8a).  Two flavours:
-
-* ``mode="hf_init"`` follows the distributions of ``CLIPPreTrainedModel._init_weights``
-  (TF:modeling_clip.py:402-459): zero biases, unit LayerNorm gains.
-* ``mode="rich"`` additionally draws non-zero biases and non-trivial LayerNorm gain/shift so that
-  every bias / affine code path of the kernels is exercised (strictly stronger test).
-
-The generator is ``torch.Generator`` on CPU: bit-reproducible for a given torch version.
-"""
-from __future__ import annotations
-
-from collections import OrderedDict
-
-import torch
-
-VISION = dict(dim=768, heads=12, ff=3072, layers=12, seq=50, patch=32, image=224)
-TEXT = dict(dim=512, heads=8, ff=2048, layers=12, seq=77, vocab=49408)
-PROJ = 512
-LOGIT_SCALE_INIT = 2.6592  # TF:configuration_clip.py:160-161
-BOS, EOS = 49406, 49407
-
-
-def _tower(sd, g, prefix: str, dim: int, ff: int, layers: int, rich: bool) -> None:
-    def randn(*shape, std):
-        return torch.randn(*shape, generator=g) * std
-
-    in_proj_std = dim ** -0.5 * (2 * layers) ** -0.5
-    out_proj_std = dim ** -0.5
-    fc_std = (2 * dim) ** -0.5
-    b_std = 0.02 if rich else 0.0
-    for i in range(layers):
-        p = f"{prefix}.encoder.layers.{i}"
-        for name in ("k_proj", "v_proj", "q_proj"):  # HF parameter order inside CLIPAttention
-            sd[f"{p}.self_attn.{name}.weight"] = randn(dim, dim, std=in_proj_std)
-            sd[f"{p}.self_attn.{name}.bias"] = randn(dim, std=b_std)
-        sd[f"{p}.self_attn.out_proj.weight"] = randn(dim, dim, std=out_proj_std)
-        sd[f"{p}.self_attn.out_proj.bias"] = randn(dim, std=b_std)
-        sd[f"{p}.layer_norm1.weight"] = 1.0 + randn(dim, std=0.1 if rich else 0.0)
-        sd[f"{p}.layer_norm1.bias"] = randn(dim, std=0.05 if rich else 0.0)
-        sd[f"{p}.mlp.fc1.weight"] = randn(ff, dim, std=fc_std)
-        sd[f"{p}.mlp.fc1.bias"] = randn(ff, std=b_std)
-        sd[f"{p}.mlp.fc2.weight"] = randn(dim, ff, std=in_proj_std)
-        sd[f"{p}.mlp.fc2.bias"] = randn(dim, std=b_std)
-        sd[f"{p}.layer_norm2.weight"] = 1.0 + randn(dim, std=0.1 if rich else 0.0)
-        sd[f"{p}.layer_norm2.bias"] = randn(dim, std=0.05 if rich else 0.0)
-
-
-def make_state_dict(seed: int = 0, mode: str = "rich") -> "OrderedDict[str, torch.Tensor]":
-    """fp32 state dict with the HF ``CLIPModel`` key set (``load_state_dict(strict=True)``-able)."""
-    assert mode in ("rich", "hf_init")
-    rich = mode == "rich"
-    g = torch.Generator(device="cpu").manual_seed(seed)
-
-    def randn(*shape, std):
-        return torch.randn(*shape, generator=g) * std
-
-    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
-    sd["logit_scale"] = torch.tensor(LOGIT_SCALE_INIT)
-    # ---- text tower (TF:modeling_clip.py:221-258, 510-589)
-    td = TEXT["dim"]
-    sd["text_model.embeddings.token_embedding.weight"] = randn(TEXT["vocab"], td, std=0.02)
-    sd["text_model.embeddings.position_embedding.weight"] = randn(TEXT["seq"], td, std=0.02)
-    _tower(sd, g, "text_model", td, TEXT["ff"], TEXT["layers"], rich)
-    sd["text_model.final_layer_norm.weight"] = 1.0 + randn(td, std=0.1 if rich else 0.0)
-    sd["text_model.final_layer_norm.bias"] = randn(td, std=0.05 if rich else 0.0)
-    # ---- vision tower (TF:modeling_clip.py:138-218, 647-691)
-    vd = VISION["dim"]
-    sd["vision_model.embeddings.class_embedding"] = randn(vd, std=vd ** -0.5)
-    sd["vision_model.embeddings.patch_embedding.weight"] = randn(vd, 3, 32, 32, std=0.02)
-    sd["vision_model.embeddings.position_embedding.weight"] = randn(VISION["seq"], vd, std=0.02)
-    sd["vision_model.pre_layrnorm.weight"] = 1.0 + randn(vd, std=0.1 if rich else 0.0)
-    sd["vision_model.pre_layrnorm.bias"] = randn(vd, std=0.05 if rich else 0.0)
-    _tower(sd, g, "vision_model", vd, VISION["ff"], VISION["layers"], rich)
-    sd["vision_model.post_layernorm.weight"] = 1.0 + randn(vd, std=0.1 if rich else 0.0)
-    sd["vision_model.post_layernorm.bias"] = randn(vd, std=0.05 if rich else 0.0)
-    # ---- projections (TF:modeling_clip.py:784-786)
-    sd["visual_projection.weight"] = randn(PROJ, vd, std=vd ** -0.5)
-    sd["text_projection.weight"] = randn(PROJ, td, std=td ** -0.5)
-    return sd
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU baseline may import ``oracle``."""
+from plip_b200.synthetic import (BOS, EOS, LOGIT_SCALE_INIT, PROJ, TEXT, VISION, make_state_dict)  # noqa: F401

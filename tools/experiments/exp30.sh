@@ -1,0 +1,3 @@
+export PYTHONPATH=.
+timeout 900 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -3
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
