@@ -390,7 +390,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "dual tower + logits_per_image: 1024 images (224x224, bf16 NCHW) x 1024 captions (77 tokens) per "
-                               "step per GPU, ViT-B/32 PLIP geometry, seeded random weights (oracle.weights seed 0)",
+                               "step per GPU, ViT-B/32 PLIP geometry, seeded random weights (plip_b200.synthetic.make_state_dict(0))",
                    "pairs_per_step_per_gpu": PAIRS, "seq_len": 77, "parallelism": f"dp{ws}",
                    "l2_policy": "inputs alternate between 2 resident sets; pixels 308 MB/step > 126 MB L2",
                    "collective": "all_gather of text embeddings [1024,512] f32 per rank (NCCL)" if ws > 1 else "none"},
