@@ -215,6 +215,40 @@ def kernel_rooflines(eng, peaks, stream):
     return res
 
 
+def stock_pytorch_context(sd, dev):
+    """Context line: the reference's own model class, transformers.CLIPModel, moved to the same GPU
+    in bfloat16 and run through PyTorch's stock kernels (cuBLAS / SDPA) on the same step (1024 pairs).  Not the
+    optimisation target and not on any product path; skipped silently if transformers is unavailable."""
+    try:
+        from transformers import CLIPConfig, CLIPModel
+        from plip_b200 import synthetic as synth
+        m = CLIPModel(CLIPConfig())
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dev, torch.bfloat16).eval()
+        px = synth.pixel_values(PAIRS, seed=4321).to(torch.bfloat16).to(dev)
+        ids = synth.token_ids(PAIRS, seed=4322, full_length=True)[0].to(dev)
+
+        def step():
+            return m(input_ids=ids, pixel_values=px).logits_per_image
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        del m
+        torch.cuda.empty_cache()
+        return {"impl": "transformers.CLIPModel.to(cuda, bfloat16), stock PyTorch kernels", "ms_per_step": ms,
+                "pairs_per_s": PAIRS / ms * 1e3}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
+
 def run_ours(args):
     rank, local_rank, ws = _dist_env()
     if not torch.cuda.is_available():
@@ -370,6 +404,8 @@ def run_ours(args):
         towers["ncu_tensor_pipe_active_pct"] = {k: v["tensor_active_pct"] for k, v in tj.items() if isinstance(v, dict)}
     except Exception:  # noqa: BLE001
         pass
+    if not args.no_context:
+        towers["stock_pytorch_bf16_same_gpu"] = stock_pytorch_context(sd, dev)
     # ---- roofline of the dominant kernel (tcgen05 GEMM), timed alone -> burst peak
     kr = kernel_rooflines(eng, peaks, torch.cuda.current_stream().cuda_stream)
     # dominant kernel = the tcgen05 GEMM template (84 % of the step, profiles/r1f_launches_bench.csv): its four
@@ -415,6 +451,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-context", action="store_true", help="skip the stock-PyTorch-on-GPU context measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rc = run_reference(args) if args.impl == "reference" else run_ours(args)
