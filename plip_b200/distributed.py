@@ -66,6 +66,20 @@ def all_gather_rows(local: torch.Tensor, counts: Optional[Sequence[int]] = None,
     return torch.cat([recv[r * mx: r * mx + counts[r]] for r in range(ws)], dim=0)
 
 
+def all_gather_rows_async(local: torch.Tensor, group=None):
+    """Equal-sized row blocks only: start ``all_gather_into_tensor`` on NCCL's stream and return
+    ``(gathered, work)``; call ``work.wait()`` before reading ``gathered`` on the current stream.  Lets the
+    exchange (and any skew between ranks) overlap with whatever is launched in between — e.g. the vision tower
+    while the text embeddings travel."""
+    rank, ws = world()
+    if ws == 1:
+        return local, None
+    local = local.contiguous()
+    recv = torch.empty((ws * local.shape[0], *local.shape[1:]), device=local.device, dtype=local.dtype)
+    work = dist.all_gather_into_tensor(recv, local, group=group, async_op=True)
+    return recv, work
+
+
 class ShardedCLIP:
     """Batch-sharded encode + similarity flows of BASELINE.json's multi-GPU configs.
 
@@ -100,8 +114,14 @@ class ShardedCLIP:
         """cfg5: gallery and queries sharded; query embeddings are all-gathered (small: 10k x 512 fp32 =
         20.5 MB), the gallery stays sharded and each rank returns its row block of the
         ``[n_gallery, n_queries]`` similarity matrix."""
-        gal = self.encode_images(local_gallery_images)
-        q_local = self.encode_text(local_query_ids)
-        q_all = all_gather_rows(q_local, shard_counts(n_total_queries, self.world_size))
+        q_local = self.encode_text(local_query_ids)                  # queries first: their exchange overlaps the gallery
+        counts = shard_counts(n_total_queries, self.world_size)
+        if self.world_size > 1 and len(set(counts)) == 1:
+            q_all, work = all_gather_rows_async(q_local)
+            gal = self.encode_images(local_gallery_images)
+            work.wait()
+        else:
+            gal = self.encode_images(local_gallery_images)
+            q_all = all_gather_rows(q_local, counts)
         block = self.similarity(gal, q_all, self.logit_scale_exp)    # [n_gallery_local, n_queries]
         return block, gal, q_all

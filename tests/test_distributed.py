@@ -51,6 +51,11 @@ def _worker(rank, ws, port, outdir):
         assert torch.equal(gathered, imgs)
         gathered2 = D.all_gather_rows(imgs[sl].contiguous(), D.shard_counts(imgs.shape[0], ws))
         assert torch.equal(gathered2, imgs)
+        # async variant (equal blocks): result identical, usable after work.wait()
+        eq = imgs[:20].view(2, 10, 12)[rank].contiguous()
+        got, work = D.all_gather_rows_async(eq)
+        work.wait()
+        assert torch.equal(got, imgs[:20])
         # cfg4 flow
         pred, logits, all_img = sh.zero_shot(imgs[sl], classes, imgs.shape[0])
         # cfg5 flow
