@@ -76,10 +76,6 @@ inline bool first_use_on_device(unsigned long long& mask) {
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);
 
-// Same without swizzle (dense [box_rows][box_cols] smem image; used for narrow store boxes).
-int make_tmap_bf16_2d_linear(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
-                             uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);
-
 #ifdef __CUDACC__
 
 // ---------------------------------------------------------------------------

@@ -46,9 +46,7 @@ struct Cfg {
   static constexpr uint32_t STAGE = A_STAGE + B_STAGE;
   static constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   // per-warp staging blocks + double-buffered bias tile (+ double-buffered colsum tile for the LN fold)
-  // residual epilogue: + per-warp [32 rows x 64 B] staging of the bf16 copy (leaves as a TMA store)
-  static constexpr uint32_t XB_BYTES = (EPI == EPI_BIAS_RESID_F32) ? kEpiWarps * 32 * 64 : 0;
-  static constexpr uint32_t EPI_BYTES = kEpiWarps * 32 * 128 + XB_BYTES + (LN_FOLD ? 4 : 2) * BN * 4;
+  static constexpr uint32_t EPI_BYTES = kEpiWarps * 32 * 128 + (LN_FOLD ? 4 : 2) * BN * 4;
   static constexpr uint32_t BAR_BYTES = 256;
   // The dynamic smem window starts 1024-aligned (checked at kernel entry), so no alignment slack is
   // reserved: that is what lets the residual epilogues run a 6-deep 32 KB operand ring.
@@ -60,7 +58,6 @@ struct Cfg {
 
 struct GemmDev {
   int M, N, K;
-  int xb_tma;     // residual epilogue: the bf16 copy leaves through a TMA bulk store (else STG.64 per lane)
   int tma_store;  // bf16 epilogues: write the staged blocks with TMA bulk stores instead of read-back + STG
   int dbg;  // diagnostic (PLIP_GEMM_DBG): 1 = no global stores, 2 = no staging and no stores, 3 = no math either
   const float* bias;
@@ -124,8 +121,8 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, f
 
 // One accumulator tile (this warp's 32 rows x BN columns) -> global memory.
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMap* tmC, const CUtensorMap* tmX,
-                                              uint32_t xb_smem, uint32_t tmem_row_base, uint32_t stage_smem,
+__device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMap* tmC, uint32_t tmem_row_base,
+                                              uint32_t stage_smem,
                                               uint32_t bias_smem, int row_base, int col_base, int n_blk, int half,
                                               int lane, float ln_mean, float ln_rstd) {
   constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
@@ -213,14 +210,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
 #pragma unroll
     for (int i = 0; i < 8; ++i) st1[i] = st2[i] = 0.f;
     const bool emit = (EPI == EPI_BIAS_RESID_F32) && p.xb_out != nullptr;
-    const bool xb_tma = emit && p.xb_tma;
 #pragma unroll 1
     for (int blk = half; blk < BN / 32; blk += 2) {
       // 32 columns -> 128 B of fp32 per row
-      if (xb_tma) {  // the previous bulk store must have finished reading the bf16 staging block
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-      }
       const int col = col_base + blk * 32 + rb_chunk * 4;
       float* out = reinterpret_cast<float*>(p.out);
       // Residual rows are fetched before the TMEM load / staging so their DRAM latency overlaps it
@@ -257,11 +249,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
               uint2 u;
               u.x = pack_bf16x2(y.x, y.y);
               u.y = pack_bf16x2(y.z, y.w);
-              if (xb_tma)
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(xb_smem + r * 64 + rb_chunk * 8), "r"(u.x), "r"(u.y)
-                             : "memory");
-              else
-                *reinterpret_cast<uint2*>(p.xb_out + static_cast<size_t>(grow) * p.ldo + col) = u;
+              *reinterpret_cast<uint2*>(p.xb_out + static_cast<size_t>(grow) * p.ldo + col) = u;
               st1[i] += (y.x + y.y) + (y.z + y.w);
               st2[i] += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
             }
@@ -274,14 +262,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
           } else {
             *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldo + col) = v;
           }
-        }
-      }
-      if (xb_tma) {
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {  // dense [32 rows][32 bf16] image; rows past M are clipped by the tensor map
-          tma_store_2d(tmX, xb_smem, col_base + blk * 32, row_base);
-          tma_store_commit();
         }
       }
       __syncwarp();
@@ -308,7 +288,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
 template <int CG, int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX, const GemmDev p) {
+            const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
   using C = Cfg<CG, BN, EPI>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -319,8 +299,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __trap();
   }
   const uint32_t epi_base = smem_base + STAGES * C::STAGE;   // 1024-aligned: 4 x 4 KB staging blocks
-  const uint32_t xb_base = epi_base + kEpiWarps * kEpiStageBytes;    // per-warp [32 x 64 B] bf16 staging (residual epilogue)
-  const uint32_t bias_base = xb_base + C::XB_BYTES;                  // 2 x BN bias (+ 2 x BN colsum) floats
+  const uint32_t bias_base = epi_base + kEpiWarps * kEpiStageBytes;  // 2 x BN bias + 2 x BN colsum floats
   const uint32_t bar_base = smem_base + STAGES * C::STAGE + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -483,8 +462,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      epilogue_tile<BN, EPI>(p, &tmC, &tmX, xb_base + warp * 2048, trow, epi_base + warp * kEpiStageBytes,
-                             bias_base + a * BN * 4, row_base,
+      epilogue_tile<BN, EPI>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + a * BN * 4, row_base,
                              n_blk * BN, n_blk, half, lane, ln_mean, ln_rstd);
       tc_fence_before();
       __syncwarp();
@@ -495,7 +473,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       a ^= 1;
       if (a == 0) aph ^= 1u;
     }
-    if ((p.tma_store || p.xb_tma) && lane == 0) tma_store_wait_all();
+    if (p.tma_store && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -566,11 +544,6 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   static const int env_dbg = env_int("PLIP_GEMM_DBG", 0);
   p.dbg = env_dbg;
   p.tma_store = tma_store ? 1 : 0;
-  static const int env_xb_tma = env_int("PLIP_GEMM_XB_TMA", 1);
-  p.xb_tma = (EPI == EPI_BIAS_RESID_F32 && g.xb_out != nullptr && env_xb_tma != 0) ? 1 : 0;
-  CUtensorMap tmX = tmA;  // placeholder when unused
-  if (p.xb_tma)
-    if (int rc = make_tmap_bf16_2d_linear(&tmX, g.xb_out, g.M, g.N, (uint64_t)g.ldo * 2, 32, 32)) return rc;
   p.bias = g.bias; p.out = g.out; p.ldo = g.ldo; p.pos = g.pos;
   p.colsum = g.colsum; p.stats_in = g.stats_in; p.n_partials = g.n_partials;
   p.xb_out = g.xb_out; p.stats_out = g.stats_out;
@@ -580,7 +553,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   int groups = max_groups;
   if (groups > num_tiles) groups = num_tiles;
 
-  PLIP_CUDA_CHECK(launch_pdl(kern, dim3(groups * CG), dim3(kThreads), C::SMEM_BYTES, stream, CG, tmA, tmB, tmC, tmX, p));
+  PLIP_CUDA_CHECK(launch_pdl(kern, dim3(groups * CG), dim3(kThreads), C::SMEM_BYTES, stream, CG, tmA, tmB, tmC, p));
   ++g_launch_count;
   return 0;
 }

@@ -49,26 +49,6 @@ static EncodeTiledFn resolve_encode() {
   return fn;
 }
 
-int make_tmap_bf16_2d_linear(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
-                             uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols) {
-  EncodeTiledFn enc = resolve_encode();
-  if (!enc) return -1;
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {row_stride_bytes};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled (linear) failed (%d): base=%p rows=%llu cols=%llu stride=%llu box=%ux%u",
-                   (int)r, base, (unsigned long long)rows, (unsigned long long)cols,
-                   (unsigned long long)row_stride_bytes, box_rows, box_cols);
-    return -1;
-  }
-  return 0;
-}
-
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn enc = resolve_encode();
