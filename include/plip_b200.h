@@ -134,6 +134,24 @@ PLIP_API int plip_similarity_topk(const float* query_dev, int64_t n, const float
 /* L2-normalise rows in place (embedders/plip.py:53,73). */
 PLIP_API int plip_l2_normalize(float* x_dev, int64_t n, int dim, void* stream);
 
+/* Image preparation on the device: n variable-size RGB uint8 images (HWC, rows packed, image i at byte
+ * descs[i].offset of src_dev) -> tiles_dev uint8 [n,224,224,3] (the PLIP_PIX_U8_NHWC input of
+ * plip_encode_images).  Image i is resized to new_width x new_height with Pillow's antialiased bicubic filter
+ * and the 224x224 window at (left, top) of the resized image is kept — bit-identical to
+ * PIL.Image.resize((new_width,new_height), BICUBIC).crop(...), i.e. to what CLIPProcessor's resize +
+ * center_crop (plip.py:35; TF:models/clip/image_processing_clip.py:50-62) and torchvision's
+ * Resize(224, BICUBIC) + CenterCrop(224) (reproducibility/embedders/transform.py:45-52) produce before their
+ * float conversion.  descs_host is a HOST array (the caller knows the sizes from decoding); it is consumed
+ * before the call returns.  src_dev / tiles_dev are device pointers; stream-ordered, no synchronisation. */
+typedef struct plip_resize_desc {
+  int64_t offset;                 /* byte offset of the image in src_dev */
+  int32_t width, height;          /* source size */
+  int32_t new_width, new_height;  /* size after the resize (each >= 224) */
+  int32_t left, top;              /* crop origin in the resized image */
+} plip_resize_desc_t;
+PLIP_API int plip_resize_crop_u8(const void* src_dev, uint64_t src_bytes, const plip_resize_desc_t* descs_host,
+                                 int64_t n, void* tiles_dev, void* stream);
+
 /* ---- host-buffer convenience (end-to-end path; copies are inside the call) ------------------- */
 /* pixels_host / ids_host / out_host are host pointers (pinned or pageable).  The call stages
  * micro-batches through pinned buffers on two streams (H2D overlapped with compute), writes the
@@ -153,6 +171,10 @@ PLIP_API int plip_dbg_gemm(const void* A_bf16, int lda, const void* W_bf16, int 
                            const float* bias, void* out, int ldo, const float* pos, int epilogue, int cta_group,
                            int block_n, const float* colsum, const float* stats_in, int n_partials, void* xb_out,
                            float* stats_out, void* stream);
+/* Host-only: fixed-point filter row of output index xx for one axis of plip_resize_crop_u8 (the same code the
+ * kernel runs).  Returns the filter bank width ksize (or -ksize if k_cap is too small). */
+PLIP_API int plip_dbg_resize_filter(int in_size, int out_size, int xx, int32_t* k_host, int k_cap, int* xmin,
+                                    int* count);
 PLIP_API int plip_dbg_rowstats_cast(const float* x, int64_t rows, int dim, void* xb_bf16, float* stats, void* stream);
 PLIP_API int plip_dbg_layernorm(const float* x, int64_t rows, int dim, int64_t in_row_stride,
                                 const float* gamma, const float* beta, float* out_f32, void* out_bf16,

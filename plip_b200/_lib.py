@@ -33,6 +33,20 @@ class TensorInfo(C.Structure):
     ]
 
 
+class ResizeDesc(C.Structure):
+    """Mirror of ``plip_resize_desc_t`` (32 bytes; ``preprocess.RESIZE_DESC_DTYPE`` is the numpy twin)."""
+
+    _fields_ = [
+        ("offset", C.c_int64),
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("new_width", C.c_int32),
+        ("new_height", C.c_int32),
+        ("left", C.c_int32),
+        ("top", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); must list every PLIP_API symbol of include/plip_b200.h
 SIGNATURES = {
     "plip_last_error": (C.c_char_p, []),
@@ -52,9 +66,11 @@ SIGNATURES = {
     "plip_similarity": (_i, [_fp, _i64, _fp, _i64, _f, _i, _i, _fp, _i64, _vp]),
     "plip_similarity_topk": (_i, [_fp, _i64, _fp, _i64, _f, _i, _i, _i, _vp, _fp, _vp]),
     "plip_l2_normalize": (_i, [_fp, _i64, _i, _vp]),
+    "plip_resize_crop_u8": (_i, [_vp, _u64, _vp, _i64, _vp, _vp]),
     "plip_encode_images_host": (_i, [_vp, _vp, _i, _i64, _fp, _i]),
     "plip_encode_text_host": (_i, [_vp, _vp, _i, _vp, _i64, _i, _fp, _i]),
     "plip_dbg_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _fp, _vp, _i, _fp, _i, _i, _i, _fp, _fp, _i, _vp, _fp, _vp]),
+    "plip_dbg_resize_filter": (_i, [_i, _i, _i, _vp, _i, C.POINTER(_i), C.POINTER(_i)]),
     "plip_dbg_rowstats_cast": (_i, [_fp, _i64, _i, _vp, _fp, _vp]),
     "plip_dbg_layernorm": (_i, [_fp, _i64, _i, _i64, _fp, _fp, _fp, _vp, _vp]),
     "plip_dbg_attention": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _vp]),

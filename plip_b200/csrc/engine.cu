@@ -512,6 +512,21 @@ PLIP_API int plip_l2_normalize(float* x_dev, int64_t n, int dim, void* stream) {
   return launch_l2_normalize(x_dev, n, dim, static_cast<cudaStream_t>(stream));
 }
 
+PLIP_API int plip_resize_crop_u8(const void* src_dev, uint64_t src_bytes, const plip_resize_desc_t* descs_host,
+                                 int64_t n, void* tiles_dev, void* stream) {
+  PLIP_REQUIRE(src_dev && descs_host && tiles_dev, "plip_resize_crop_u8: null argument");
+  PLIP_REQUIRE(n > 0, "plip_resize_crop_u8: n must be positive (got %lld)", (long long)n);
+  return launch_resize_crop(static_cast<const uint8_t*>(src_dev), (size_t)src_bytes, descs_host, n,
+                            static_cast<uint8_t*>(tiles_dev), static_cast<cudaStream_t>(stream));
+}
+
+PLIP_API int plip_dbg_resize_filter(int in_size, int out_size, int xx, int32_t* k_host, int k_cap, int* xmin,
+                                    int* count) {
+  PLIP_REQUIRE(k_host && xmin && count && in_size > 0 && out_size > 0 && xx >= 0 && xx < out_size,
+               "plip_dbg_resize_filter: bad argument");
+  return resize_filter_host(in_size, out_size, xx, k_host, k_cap, xmin, count);
+}
+
 // ---- host-buffer path ---------------------------------------------------------------------------
 PLIP_API int plip_encode_images_host(plip_engine_t* e, const void* pixels_host, int pixel_format, int64_t n,
                                      float* out_host, int normalize) {

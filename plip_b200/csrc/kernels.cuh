@@ -20,6 +20,12 @@ int launch_mask_to_i32(const void* mask, int dtype, int64_t count, int seq_len, 
 int launch_cls_rows(const float* cls, const float* pos, int64_t n, float* x, cudaStream_t st);
 int launch_l2_normalize(float* x, int64_t rows, int dim, cudaStream_t st);
 
+// resize.cu: Pillow-exact bicubic resize + crop of packed RGB uint8 images into [n,224,224,3] tiles.
+int launch_resize_crop(const uint8_t* src, size_t src_bytes, const plip_resize_desc_t* descs_host, int64_t n,
+                       uint8_t* tiles, cudaStream_t st);
+
+int resize_filter_host(int in_size, int out_size, int xx, int32_t* k, int k_cap, int* xmin, int* count);
+
 // attention.cu: softmax(q k^T [+causal/padding mask]) v per (sequence, head); q pre-scaled by dh^-0.5.
 // qkv: bf16 [n_seq*seq_len, 3*heads*64]; key_mask: optional int32 [n_seq, seq_len] (0 = masked key).
 int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int heads, bool causal,

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from .modeling import PlipCLIPModel
-from .preprocess import chunks, to_uint8_tiles
+from .preprocess import SIZE, chunks, decode_rgb, pack_rgb, to_uint8_tiles
 
 
 class AbstractEmbedder(ABC):
@@ -61,10 +61,17 @@ class CLIPEmbedder(AbstractEmbedder):
         outs: List[torch.Tensor] = []
         eng = getattr(self.model, "engine", None)
         for chunk in chunks(list(list_of_images), max(int(batch_size), 256)):
-            tiles = to_uint8_tiles(chunk, int(num_workers))
+            # torchvision's CenterCrop rounding (transform.py:45-52), not CLIPImageProcessor's floor
             if eng is not None:
-                outs.append(eng.encode_images_host(tiles, normalize=True))
+                arrays = decode_rgb(chunk, int(num_workers))
+                if all(a.shape == (SIZE, SIZE, 3) for a in arrays):
+                    outs.append(eng.encode_images_host(np.stack(arrays, axis=0), normalize=True))
+                else:  # Pillow-exact bicubic resize + crop on the device
+                    buf, descs = pack_rgb(arrays, crop="round", pinned=True)
+                    tiles = eng.resize_crop(buf.to(eng.device, non_blocking=True), descs)
+                    outs.append(eng.encode_images(tiles, normalize=True).cpu())
             else:  # any OpenAI-clip-like model
+                tiles = to_uint8_tiles(chunk, int(num_workers), crop="round")
                 t = torch.from_numpy(tiles).to(device)
                 e = self.model.encode_image(t).detach().float().cpu()
                 outs.append(e / e.norm(dim=1, keepdim=True))

@@ -187,6 +187,23 @@ class Engine:
                       "plip_l2_normalize")
         return x
 
+    @torch.no_grad()
+    def resize_crop(self, src: torch.Tensor, descs: np.ndarray, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Packed RGB uint8 images on the device + host descriptors (``preprocess.pack_rgb``) -> uint8 tiles
+        ``[n,224,224,3]``; Pillow-exact bicubic resize and crop (``plip_resize_crop_u8``)."""
+        from .preprocess import RESIZE_DESC_DTYPE
+        assert src.is_cuda and src.dtype == torch.uint8 and src.is_contiguous() and src.dim() == 1
+        descs = np.ascontiguousarray(descs, dtype=RESIZE_DESC_DTYPE)
+        n = int(descs.shape[0])
+        if out is None:
+            out = torch.empty((n, 224, 224, 3), device=src.device, dtype=torch.uint8)
+        assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == n * 224 * 224 * 3
+        if n:
+            with torch.cuda.device(src.device):
+                check(self._L.plip_resize_crop_u8(src.data_ptr(), int(src.numel()), descs.ctypes.data, n,
+                                                  out.data_ptr(), self._stream()), "plip_resize_crop_u8")
+        return out
+
     # ---- host-buffer API (copies inside the call) ------------------------------------------------
     def encode_images_host(self, pixels: Union[np.ndarray, torch.Tensor], normalize: bool = False,
                            out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -21,19 +21,20 @@ import torch
 from tqdm import tqdm
 
 from .modeling import PlipCLIPModel
-from .preprocess import chunks, to_uint8_tiles
+from .preprocess import SIZE, chunks, decode_rgb, pack_rgb, to_uint8_tiles
 
 
 class PLIP:
 
     def __init__(self, model_name, auth_token=None, *, model: Optional[PlipCLIPModel] = None, preprocess=None,
-                 max_micro_batch: int = 1024, num_workers: int = 0):
+                 max_micro_batch: int = 1024, num_workers: int = 0, device_resize: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("plip_b200.PLIP needs a CUDA device; there is no CPU fallback")
         self.device = "cuda"
         self.model_name = model_name
         self.max_micro_batch = max_micro_batch
         self.num_workers = int(num_workers)      # host threads for image decode / resize (0 = in-line)
+        self.device_resize = bool(device_resize)  # images that are not 224x224: resize on the GPU (else PIL)
         if model is not None:
             self.model, self.preprocess, self.model_hash = model, preprocess, hash
         else:
@@ -65,24 +66,30 @@ class PLIP:
         eng = self.model.engine
         flush = max(int(batch_size), eng.max_micro_batch)
         out = np.empty((len(images), 512), dtype=np.float32)
-        pending: List[np.ndarray] = []
-        n_pending, done = 0, 0
+        pending: List[np.ndarray] = []   # decoded RGB arrays, any size
+        done = 0
         pbar = tqdm(total=len(images) // batch_size, position=0)
 
         def _flush():
-            nonlocal pending, n_pending, done
+            nonlocal pending, done
             if not pending:
                 return
-            tiles = pending[0] if len(pending) == 1 else np.concatenate(pending, axis=0)
-            res = eng.encode_images_host(tiles)
-            out[done:done + n_pending] = res.numpy()
-            done += n_pending
-            pending, n_pending = [], 0
+            if all(a.shape == (SIZE, SIZE, 3) for a in pending):
+                res = eng.encode_images_host(np.stack(pending, axis=0)).numpy()
+            elif self.device_resize:
+                # upload the decoded images once; Pillow-exact bicubic resize + centre crop on the device
+                buf, descs = pack_rgb(pending, crop="floor", pinned=True)
+                tiles = eng.resize_crop(buf.to(eng.device, non_blocking=True), descs)
+                res = eng.encode_images(tiles).cpu().numpy()
+            else:
+                res = eng.encode_images_host(to_uint8_tiles(pending, self.num_workers)).numpy()
+            out[done:done + len(pending)] = res
+            done += len(pending)
+            pending = []
 
         for chunk in chunks(images, int(batch_size)):
-            pending.append(to_uint8_tiles(chunk, self.num_workers))
-            n_pending += len(chunk)
-            if n_pending >= flush:
+            pending.extend(decode_rgb(chunk, self.num_workers))
+            if len(pending) >= flush:
                 _flush()
             pbar.update(1)
         _flush()
