@@ -9,21 +9,26 @@
 // bit-identical to PIL.Image.resize(...).crop(...) (tests/test_resize.py): the weights are rebuilt on the device
 // with the same sequence of IEEE double operations (explicit _rn intrinsics: no FMA contraction).
 //
-// One CTA produces 8 output rows of one tile.  It builds the 224 horizontal filter rows it needs (only the
-// cropped columns) and its 8 vertical ones in shared memory, then for `rows_per_pass` output rows at a time
-// runs the horizontal pass over the source rows those outputs touch into a uint8 shared-memory strip and the
-// vertical pass out of that strip.  Source pixels are read from HBM once per CTA strip (strips of adjacent CTAs
-// overlap by the filter support); the roofline is HBM: source bytes + 150,528 tile bytes per image.
+// One CTA produces 32 output rows of one tile (7 CTAs per image).  Its 256 threads first build the 224
+// horizontal filter rows it needs (only the cropped columns) and its 32 vertical ones in shared memory, zero-padded
+// to a multiple of 4 taps.  Then, for `rows_per_pass` output rows at a time, the horizontal pass runs over the
+// source rows those outputs touch — one thread per (row, column), all 3 channels, source bytes fetched as aligned
+// 32-bit words and re-aligned with funnel shifts (4 pixels = 3 words per step, weights as one 16-byte shared load)
+// — into a uint8 shared-memory strip, and the vertical pass runs out of that strip, one thread per 4 output bytes.
+// Source pixels are read once per strip (strips overlap by the filter support; L2 absorbs the re-reads); the
+// roofline is HBM (source bytes + 150,528 tile bytes per image) but the kernel is issue-bound: H_src x 224 x 3 x
+// taps integer MACs per image with ~3 instructions each (profiles/r1_resize_probe.json).
 #include "kernels.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace plip {
 
 namespace {
 
 constexpr int kRsThreads = 256;
-constexpr int kRsRowsPerCta = 8;
+constexpr int kRsRowsPerCta = 32;
 constexpr int kRsBatch = 64;                 // images per launch (descriptors travel as kernel parameters)
 constexpr int kTileRowBytes = kImage * 3;    // 672
 constexpr int kPrecisionBits = 32 - 8 - 2;   // Pillow's PRECISION_BITS for 8-bit channels
@@ -33,7 +38,7 @@ struct ResizeImg {
   int w, h;            // source size
   int new_w, new_h;    // size after the resize
   int left, top;       // crop origin in the resized image
-  int rows_per_pass;   // output rows per strip (8, 4, 2 or 1)
+  int rows_per_pass;   // output rows per strip (32, 16, ... or 1)
   int strip_rows;      // capacity of the uint8 strip, in source rows
 };
 
@@ -106,12 +111,51 @@ __host__ __device__ __forceinline__ void filter_row(const AxisFilter& f, int in_
   count_out = count;
 }
 
-__device__ __forceinline__ uint8_t clip8(int acc) {
+__device__ __forceinline__ uint32_t clip8(int acc) {
   const int v = acc >> kPrecisionBits;
-  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+  return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-__global__ void __launch_bounds__(kRsThreads) resize_crop_kernel(const uint8_t* __restrict__ src,
+__device__ __forceinline__ int byte_of(uint32_t w, int i) { return (int)__byte_perm(w, 0, 0x4440 + i); }
+
+// Aligned 32-bit read of the source; the last (partial) word of the buffer is assembled from its valid bytes.
+template <bool GUARD>
+__device__ __forceinline__ uint32_t src_word(const uint32_t* q, const uint32_t* end_w, const uint8_t* end_b) {
+  if (!GUARD || q < end_w) return __ldg(q);
+  uint32_t w = 0;
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (b + i < end_b) w |= (uint32_t)__ldg(b + i) << (8 * i);
+  return w;
+}
+
+// One output pixel of the horizontal pass: 3 channels x `cnt4` taps (a multiple of 4; weights beyond the window
+// are zero).  The window's bytes are fetched as aligned words and re-aligned with a funnel shift, 4 pixels (three
+// words) per step.
+template <bool GUARD>
+__device__ __forceinline__ void hpass_pixel(const uint8_t* p, const int* __restrict__ k, int cnt4,
+                                            const uint32_t* end_w, const uint8_t* end_b, int& a0, int& a1, int& a2) {
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(p - mis);
+  const uint32_t sh = mis * 8;
+  uint32_t prev = src_word<GUARD>(wp, end_w, end_b);
+  const int4* k4 = reinterpret_cast<const int4*>(k);
+  for (int x = 0; x < cnt4; x += 4) {
+    const uint32_t w1 = src_word<GUARD>(wp + 1, end_w, end_b), w2 = src_word<GUARD>(wp + 2, end_w, end_b),
+                   w3 = src_word<GUARD>(wp + 3, end_w, end_b);
+    const uint32_t s0 = __funnelshift_r(prev, w1, sh), s1 = __funnelshift_r(w1, w2, sh),
+                   s2 = __funnelshift_r(w2, w3, sh);
+    prev = w3;
+    wp += 3;
+    const int4 kk = *k4++;
+    a0 += byte_of(s0, 0) * kk.x + byte_of(s0, 3) * kk.y + byte_of(s1, 2) * kk.z + byte_of(s2, 1) * kk.w;
+    a1 += byte_of(s0, 1) * kk.x + byte_of(s1, 0) * kk.y + byte_of(s1, 3) * kk.z + byte_of(s2, 2) * kk.w;
+    a2 += byte_of(s0, 2) * kk.x + byte_of(s1, 1) * kk.y + byte_of(s2, 0) * kk.z + byte_of(s2, 3) * kk.w;
+  }
+}
+
+__global__ void __launch_bounds__(kRsThreads) resize_crop_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
                                                                  uint8_t* __restrict__ tiles, const ResizeBatch batch,
                                                                  int64_t first_image) {
   extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -120,68 +164,89 @@ __global__ void __launch_bounds__(kRsThreads) resize_crop_kernel(const uint8_t* 
   const ResizeImg& im = batch.img[blockIdx.y];
   const int row0 = blockIdx.x * kRsRowsPerCta;  // first output row of this CTA
   const AxisFilter fh = make_axis(im.w, im.new_w), fv = make_axis(im.h, im.new_h);
+  const int ksh4 = (fh.ksize + 3) & ~3, ksv4 = (fv.ksize + 3) & ~3;  // filter rows zero-padded to 4 taps
 
-  int* kh = reinterpret_cast<int*>(rs_smem);                 // [224][ksize_h]
-  int* kv = kh + kImage * fh.ksize;                          // [8][ksize_v]
-  int* bh = kv + kRsRowsPerCta * fv.ksize;                   // [224][2] (xmin, count)
-  int* bv = bh + kImage * 2;                                 // [8][2]
-  uint8_t* strip = reinterpret_cast<uint8_t*>(bv + kRsRowsPerCta * 2);  // [strip_rows][224*3]
+  int* kh = reinterpret_cast<int*>(rs_smem);                 // [224][ksh4]
+  int* kv = kh + kImage * ksh4;                              // [32][ksv4]
+  int* bh = kv + kRsRowsPerCta * ksv4;                       // [224][2] (xmin, count)
+  int* bv = bh + kImage * 2;                                 // [32][2]
+  uint8_t* strip = reinterpret_cast<uint8_t*>(bv + kRsRowsPerCta * 2);  // [strip_rows + 3][224*3], 16-byte aligned
 
   const int t = threadIdx.x;
-  if (t < kImage) {
-    int xmin, cnt;
-    filter_row(fh, im.w, im.left + t, kh + t * fh.ksize, xmin, cnt);
-    bh[2 * t] = xmin;
-    bh[2 * t + 1] = cnt;
-  } else if (t < kImage + kRsRowsPerCta) {
-    const int j = t - kImage;
-    int ymin, cnt;
-    filter_row(fv, im.h, im.top + row0 + j, kv + j * fv.ksize, ymin, cnt);
-    bv[2 * j] = ymin;
-    bv[2 * j + 1] = cnt;
+  {
+    const bool horiz = t < kImage;
+    const int j = horiz ? t : t - kImage;
+    int* k = horiz ? kh + j * ksh4 : kv + j * ksv4;
+    int lo, cnt;
+    if (horiz)
+      filter_row(fh, im.w, im.left + j, k, lo, cnt);
+    else
+      filter_row(fv, im.h, im.top + row0 + j, k, lo, cnt);
+    for (int x = cnt; x < (horiz ? ksh4 : ksv4); ++x) k[x] = 0;
+    int* bnd = horiz ? bh + 2 * j : bv + 2 * j;
+    bnd[0] = lo;
+    bnd[1] = cnt;
   }
   __syncthreads();
 
   const uint8_t* img = src + im.src_off;
   const int64_t src_row_bytes = (int64_t)im.w * 3;
+  const uint8_t* end_b = src + src_bytes;
+  const uint32_t* end_w = reinterpret_cast<const uint32_t*>(src + (src_bytes & ~(uint64_t)3));  // src is 4-aligned
   uint8_t* out = tiles + ((first_image + blockIdx.y) * kImage + row0) * (int64_t)kTileRowBytes;
   const int rp = im.rows_per_pass;
+  constexpr int kRowWords = kTileRowBytes / 4;  // 168
   for (int sub = 0; sub < kRsRowsPerCta; sub += rp) {
     const int s0 = bv[2 * sub];
     const int s1 = bv[2 * (sub + rp - 1)] + bv[2 * (sub + rp - 1) + 1];
     const int nrows = s1 - s0;
     if (nrows > im.strip_rows) __trap();  // host sizing bug: never expected
-    // horizontal pass: strip[r][xx][c] for the source rows [s0, s1)
-    for (int idx = t; idx < nrows * kTileRowBytes; idx += kRsThreads) {
-      const int r = idx / kTileRowBytes, e = idx - r * kTileRowBytes;
-      const int xx = e / 3, c = e - xx * 3;
-      const int xmin = bh[2 * xx], cnt = bh[2 * xx + 1];
-      const uint8_t* p = img + (int64_t)(s0 + r) * src_row_bytes + (int64_t)xmin * 3 + c;
-      const int* k = kh + xx * fh.ksize;
-      int acc = 1 << (kPrecisionBits - 1);
-      for (int x = 0; x < cnt; ++x) acc += (int)__ldg(p + x * 3) * k[x];
-      strip[idx] = clip8(acc);
+    // horizontal pass: strip[r][xx][0..2] for the source rows [s0, s1); one thread per (row, column)
+    for (int idx = t; idx < nrows * kImage; idx += kRsThreads) {
+      const int r = idx / kImage, xx = idx - r * kImage;
+      const int xmin = bh[2 * xx], cnt4 = (bh[2 * xx + 1] + 3) & ~3;
+      const uint8_t* p = img + (int64_t)(s0 + r) * src_row_bytes + (int64_t)xmin * 3;
+      const int* k = kh + xx * ksh4;
+      int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+      // words read: [p & ~3, ... + 3*cnt4 + 4) bytes; only the very end of the source buffer needs the guard
+      if (p + 3 * cnt4 + 8 <= reinterpret_cast<const uint8_t*>(end_w))
+        hpass_pixel<false>(p, k, cnt4, end_w, end_b, a0, a1, a2);
+      else
+        hpass_pixel<true>(p, k, cnt4, end_w, end_b, a0, a1, a2);
+      uint8_t* d = strip + r * kTileRowBytes + xx * 3;
+      d[0] = (uint8_t)clip8(a0);
+      d[1] = (uint8_t)clip8(a1);
+      d[2] = (uint8_t)clip8(a2);
     }
     __syncthreads();
-    // vertical pass: rp output rows out of the strip
-    for (int idx = t; idx < rp * kTileRowBytes; idx += kRsThreads) {
-      const int j = idx / kTileRowBytes, e = idx - j * kTileRowBytes;
-      const int ymin = bv[2 * (sub + j)], cnt = bv[2 * (sub + j) + 1];
-      const uint8_t* p = strip + (ymin - s0) * kTileRowBytes + e;
-      const int* k = kv + (sub + j) * fv.ksize;
-      int acc = 1 << (kPrecisionBits - 1);
-      for (int y = 0; y < cnt; ++y) acc += (int)p[y * kTileRowBytes] * k[y];
-      out[(sub + j) * kTileRowBytes + e] = clip8(acc);
+    // vertical pass: rp output rows out of the strip; one thread per 4 output bytes
+    for (int idx = t; idx < rp * kRowWords; idx += kRsThreads) {
+      const int j = idx / kRowWords, e = idx - j * kRowWords;
+      const int ymin = bv[2 * (sub + j)], cnt4 = (bv[2 * (sub + j) + 1] + 3) & ~3;
+      const uint32_t* sp = reinterpret_cast<const uint32_t*>(strip + (ymin - s0) * kTileRowBytes) + e;
+      const int4* k4 = reinterpret_cast<const int4*>(kv + (sub + j) * ksv4);
+      int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0;
+      for (int y = 0; y < cnt4; y += 4) {   // taps beyond the window have zero weight (rows exist: strip has +3)
+        const int4 kk = *k4++;
+        const uint32_t w0 = sp[0], w1 = sp[kRowWords], w2 = sp[2 * kRowWords], w3 = sp[3 * kRowWords];
+        sp += 4 * kRowWords;
+        a0 += byte_of(w0, 0) * kk.x + byte_of(w1, 0) * kk.y + byte_of(w2, 0) * kk.z + byte_of(w3, 0) * kk.w;
+        a1 += byte_of(w0, 1) * kk.x + byte_of(w1, 1) * kk.y + byte_of(w2, 1) * kk.z + byte_of(w3, 1) * kk.w;
+        a2 += byte_of(w0, 2) * kk.x + byte_of(w1, 2) * kk.y + byte_of(w2, 2) * kk.z + byte_of(w3, 2) * kk.w;
+        a3 += byte_of(w0, 3) * kk.x + byte_of(w1, 3) * kk.y + byte_of(w2, 3) * kk.z + byte_of(w3, 3) * kk.w;
+      }
+      reinterpret_cast<uint32_t*>(out + (sub + j) * kTileRowBytes)[e] =
+          clip8(a0) | (clip8(a1) << 8) | (clip8(a2) << 16) | (clip8(a3) << 24);
     }
     __syncthreads();
   }
 }
 
-constexpr size_t kRsSmemSoft = 96 * 1024;    // preferred ceiling: two CTAs per SM
 constexpr size_t kRsSmemHard = 200 * 1024;
 
 size_t table_bytes(int ksh, int ksv) {
-  return ((size_t)kImage * ksh + (size_t)kRsRowsPerCta * ksv + (kImage + kRsRowsPerCta) * 2) * sizeof(int);
+  const size_t ksh4 = (ksh + 3) & ~3, ksv4 = (ksv + 3) & ~3;
+  return ((size_t)kImage * ksh4 + (size_t)kRsRowsPerCta * ksv4 + (kImage + kRsRowsPerCta) * 2) * sizeof(int);
 }
 
 // Source rows one strip of `rp` output rows can touch: (rp-1)*scale + 2*support + rounding slack.
@@ -191,6 +256,8 @@ int strip_rows_for(int in_h, int out_h, int rp) {
   int rows = (int)ceil((rp - 1) * scale + 2.0 * support) + 3;
   return rows > in_h ? in_h : rows;
 }
+
+constexpr int kStripPadRows = 3;  // the vertical pass reads whole groups of 4 rows
 
 }  // namespace
 
@@ -207,6 +274,8 @@ int launch_resize_crop(const uint8_t* src, size_t src_bytes, const plip_resize_d
   if (first_use_on_device(configured))
     PLIP_CUDA_CHECK(cudaFuncSetAttribute(resize_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kRsSmemHard));
+  PLIP_REQUIRE(reinterpret_cast<uintptr_t>(src) % 4 == 0 && reinterpret_cast<uintptr_t>(tiles) % 4 == 0,
+               "plip_resize_crop_u8: src_dev and tiles_dev must be 4-byte aligned");
   for (int64_t base = 0; base < n; base += kRsBatch) {
     const int cnt = (int)((n - base) < kRsBatch ? (n - base) : kRsBatch);
     ResizeBatch b = {};
@@ -227,13 +296,22 @@ int launch_resize_crop(const uint8_t* src, size_t src_bytes, const plip_resize_d
                    s.top, s.new_width, s.new_height);
       const int ksh = axis_ksize(s.width, s.new_width), ksv = axis_ksize(s.height, s.new_height);
       const size_t tb = table_bytes(ksh, ksv);
+      // Strip height: taller strips re-read fewer source rows (adjacent strips overlap by the filter support),
+      // shorter ones need less shared memory and keep more CTAs per SM.  Relative throughput by resident CTAs
+      // measured on B200 (profiles/r1_resize_probe.json); registers cap residency at 5.
+      static const double kThroughput[6] = {0.0, 1.0, 1.12, 1.21, 1.57, 1.70};
+      const double vscale = (double)s.height / (double)s.new_height, fs = vscale < 1.0 ? 1.0 : vscale;
       int rp = 0, rows = 0;
-      for (size_t limit : {kRsSmemSoft, kRsSmemHard}) {
-        for (int cand = kRsRowsPerCta; cand >= 1 && !rp; cand >>= 1) {
-          const int r = strip_rows_for(s.height, s.new_height, cand);
-          if (tb + (size_t)r * kTileRowBytes <= limit) rp = cand, rows = r;
-        }
-        if (rp) break;
+      double best = 0.0;
+      for (int cand = kRsRowsPerCta; cand >= 1; cand >>= 1) {
+        const int r = strip_rows_for(s.height, s.new_height, cand);
+        const size_t need = tb + (size_t)(r + kStripPadRows) * kTileRowBytes;
+        if (need > kRsSmemHard) continue;
+        int resident = (int)((size_t)227 * 1024 / (need + 1024));
+        resident = resident > 5 ? 5 : resident;
+        const double reread = ((cand - 1) * vscale + 4.0 * fs + 1.0) / (cand * vscale);
+        const double score = kThroughput[resident] / reread;
+        if (score > best) best = score, rp = cand, rows = r;
       }
       PLIP_REQUIRE(rp, "plip_resize_crop_u8: image %lld (%dx%d -> %dx%d) shrinks too much for the on-device "
                    "resize (filter tables need %zu bytes of shared memory); reduce it on the host first",
@@ -242,11 +320,11 @@ int launch_resize_crop(const uint8_t* src, size_t src_bytes, const plip_resize_d
       o.src_off = s.offset;
       o.w = s.width, o.h = s.height, o.new_w = s.new_width, o.new_h = s.new_height;
       o.left = s.left, o.top = s.top, o.rows_per_pass = rp, o.strip_rows = rows;
-      const size_t need = tb + (size_t)rows * kTileRowBytes;
+      const size_t need = tb + (size_t)(rows + kStripPadRows) * kTileRowBytes;
       smem = need > smem ? need : smem;
     }
     PLIP_CUDA_CHECK(launch_pdl(resize_crop_kernel, dim3(kImage / kRsRowsPerCta, cnt), dim3(kRsThreads), smem, st, 1,
-                               src, tiles, b, base));
+                               src, (uint64_t)src_bytes, tiles, b, base));
     ++g_launch_count;
   }
   return 0;
