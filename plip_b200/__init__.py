@@ -8,13 +8,14 @@ Python host code over a hand-written sm_100a CUDA library (``libplip_b200.so``, 
   ``model(**inputs).logits_per_image`` and OpenAI-clip ``encode_image`` / ``encode_text``
 * :class:`plip_b200.embedders.CLIPEmbedder` / ``EmbedderFactory`` — ``reproducibility/embedders``
 * :class:`plip_b200.engine.Engine` — the raw engine handle; :mod:`plip_b200.distributed` — multi-GPU sharding
+* :class:`plip_b200.tokenizer.ClipTokenizer` — CLIP byte-level BPE (HF ``vocab.json``/``merges.txt`` or OpenAI merge file)
 
 Importing the package does not load the CUDA library; the first engine / packer call does and raises if it
 is missing (there is no CPU fallback).
 """
 __version__ = "0.1.0"
 
-__all__ = ["PLIP", "PlipCLIPModel", "CLIPOutput", "CLIPEmbedder", "EmbedderFactory", "Engine"]
+__all__ = ["PLIP", "PlipCLIPModel", "CLIPOutput", "CLIPEmbedder", "EmbedderFactory", "Engine", "ClipTokenizer"]
 
 
 def __getattr__(name):
@@ -30,4 +31,7 @@ def __getattr__(name):
     if name == "Engine":
         from .engine import Engine
         return Engine
+    if name == "ClipTokenizer":
+        from .tokenizer import ClipTokenizer
+        return ClipTokenizer
     raise AttributeError(name)

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from .modeling import PlipCLIPModel
+from .tokenizer import find_tokenizer
 from .preprocess import SIZE, chunks, decode_rgb, pack_rgb, to_uint8_tiles
 
 
@@ -33,12 +34,18 @@ class AbstractEmbedder(ABC):
         ...
 
 
-def _default_tokenize() -> Optional[Callable]:
+def _default_tokenize(*asset_dirs) -> Optional[Callable]:
+    """``clip.tokenize(captions, truncate=True)`` (``embedders/plip.py:65``): the OpenAI package when installed,
+    else the built-in BPE on merge-table assets found next to the checkpoint or via ``$PLIP_B200_TOKENIZER``."""
     try:
         import clip  # OpenAI clip package (not installed in this image; SURVEY.md §8c)
         return lambda captions: clip.tokenize(captions, truncate=True)
     except Exception:  # noqa: BLE001
+        pass
+    tok = find_tokenizer(*asset_dirs)
+    if tok is None:
         return None
+    return lambda captions: torch.from_numpy(tok.tokenize(list(captions), truncate=True))
 
 
 class CLIPEmbedder(AbstractEmbedder):
@@ -48,7 +55,8 @@ class CLIPEmbedder(AbstractEmbedder):
         self.preprocess = preprocess  # kept for API parity; tiles are prepared by plip_b200.preprocess
         self.name = name
         self.backbone = backbone
-        self.tokenize = tokenize or _default_tokenize()
+        self.tokenize = tokenize or _default_tokenize(
+            os.path.dirname(backbone) if isinstance(backbone, str) and backbone else None)
 
     def image_embedder(self, list_of_images, device="cuda", num_workers=1, batch_size=32, additional_cache_name=""):
         return self.embed_images(list_of_images, device=device, num_workers=num_workers, batch_size=batch_size)
@@ -84,8 +92,9 @@ class CLIPEmbedder(AbstractEmbedder):
             idx = torch.as_tensor(np.asarray(labels))
         else:
             if self.tokenize is None:
-                raise RuntimeError("no tokenizer available (the `clip` package is not installed): pass a "
-                                   "`tokenize` callable or pre-tokenised id rows")
+                raise RuntimeError("no tokenizer available (the `clip` package is not installed and no merge table was "
+                                   "found next to the checkpoint or in $PLIP_B200_TOKENIZER): pass a `tokenize` "
+                                   "callable or pre-tokenised id rows")
             idx = self.tokenize(labels)
         outs = []
         for chunk in chunks(idx, max(int(batch_size), 1024)):

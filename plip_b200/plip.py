@@ -13,6 +13,7 @@ Results: float32 ``[N,512]`` numpy arrays, un-normalised, order-preserving — a
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Union
 
 import numpy as np
@@ -21,13 +22,14 @@ import torch
 from tqdm import tqdm
 
 from .modeling import PlipCLIPModel
+from .tokenizer import find_tokenizer
 from .preprocess import SIZE, chunks, decode_rgb, pack_rgb, to_uint8_tiles
 
 
 class PLIP:
 
     def __init__(self, model_name, auth_token=None, *, model: Optional[PlipCLIPModel] = None, preprocess=None,
-                 max_micro_batch: int = 1024, num_workers: int = 0, device_resize: bool = True):
+                 max_micro_batch: int = 1024, num_workers: int = 0, device_resize: bool = True, tokenizer=None):
         if not torch.cuda.is_available():
             raise RuntimeError("plip_b200.PLIP needs a CUDA device; there is no CPU fallback")
         self.device = "cuda"
@@ -40,13 +42,17 @@ class PLIP:
         else:
             self.model, self.preprocess, self.model_hash = self._load_model(model_name, auth_token=auth_token)
         self.model = self.model.to(self.device)
+        # string captions: the checkpoint's vocab.json + merges.txt (or $PLIP_B200_TOKENIZER) through the built-in BPE
+        self.tokenizer = tokenizer if tokenizer is not None else find_tokenizer(
+            model_name if isinstance(model_name, str) and os.path.isdir(model_name) else None)
         self.image_vectors = None  # the reference reads this in retrieval() without ever setting it
 
     @classmethod
-    def from_state_dict(cls, state_dict, preprocess=None, model_name="state_dict", max_micro_batch: int = 1024):
+    def from_state_dict(cls, state_dict, preprocess=None, model_name="state_dict", max_micro_batch: int = 1024,
+                        tokenizer=None):
         """Build from an in-memory HF / OpenAI-clip state dict (no checkpoint directory needed)."""
         return cls(model_name, model=PlipCLIPModel(state_dict, max_micro_batch=max_micro_batch),
-                   preprocess=preprocess, max_micro_batch=max_micro_batch)
+                   preprocess=preprocess, max_micro_batch=max_micro_batch, tokenizer=tokenizer)
 
     def _load_model(self, name: str, device: Union[str, torch.device] = "cuda", auth_token=None):
         model = PlipCLIPModel.from_pretrained(name, max_micro_batch=self.max_micro_batch, use_auth_token=auth_token)
@@ -55,6 +61,10 @@ class PLIP:
             from transformers import CLIPProcessor
             preprocessing = CLIPProcessor.from_pretrained(name, **({"token": auth_token} if auth_token else {}))
         except Exception:  # noqa: BLE001 - a checkpoint dir without tokenizer assets still encodes images / ids
+            preprocessing = None
+        tok = getattr(preprocessing, "tokenizer", None)
+        if tok is not None and len(tok) < 49408:
+            # without vocab.json / merges.txt transformers silently builds a 3-token tokenizer
             preprocessing = None
         return model, preprocessing, hash
 
@@ -97,8 +107,12 @@ class PLIP:
         return out
 
     def _tokenize(self, text: List[str]):
-        if self.preprocess is None:
-            raise RuntimeError("no tokenizer available for this checkpoint: pass token ids to encode_token_ids()")
+        if self.preprocess is None and self.tokenizer is None:
+            raise RuntimeError("no tokenizer available for this checkpoint (no vocab.json + merges.txt next to it, "
+                               "$PLIP_B200_TOKENIZER unset): pass token ids to encode_token_ids()")
+        if self.tokenizer is not None:   # built-in byte-level BPE on the checkpoint's own vocabulary
+            enc = self.tokenizer(list(text), return_tensors="pt", max_length=77, padding="max_length", truncation=True)
+            return enc["input_ids"], enc["attention_mask"]
         enc = self.preprocess(text=list(text), return_tensors="pt", max_length=77, padding="max_length",
                               truncation=True)  # plip.py:57-58
         return enc["input_ids"], enc.get("attention_mask")
