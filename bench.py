@@ -22,6 +22,7 @@ import sys
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -411,6 +412,20 @@ def run_ours(args):
         pass
     if not args.no_context:
         towers["stock_pytorch_bf16_same_gpu"] = stock_pytorch_context(sd, dev)
+    try:  # image preparation on the device: 1024 decoded 256x256 RGB images -> 224x224 tiles
+        from plip_b200 import preprocess as P
+        rs_rng = np.random.default_rng(7)
+        base = [rs_rng.integers(0, 256, (256, 256, 3), dtype=np.uint8) for _ in range(8)]
+        rs_buf, rs_desc = P.pack_rgb([base[i % 8] for i in range(PAIRS)])
+        rs_src = rs_buf.to(dev)
+        rs_out = eng.resize_crop(rs_src, rs_desc)
+        ms_r = tower(lambda: eng.resize_crop(rs_src, rs_desc, out=rs_out))
+        rs_bytes = int(rs_src.numel()) + PAIRS * 224 * 224 * 3
+        towers["device_resize_1024x256x256"] = {"ms": ms_r, "us_per_image": ms_r * 1e3 / PAIRS, "bound": "hbm",
+                                                "algorithmic_bytes": rs_bytes, "GBps": rs_bytes / ms_r / 1e6,
+                                                "frac_of_hbm_peak": rs_bytes / ms_r / 1e6 / peaks["hbm_gbs"]}
+    except Exception as exc:  # noqa: BLE001 - context only
+        towers["device_resize_1024x256x256"] = {"error": str(exc)}
     # ---- roofline of the dominant kernel (tcgen05 GEMM), timed alone -> burst peak
     kr = kernel_rooflines(eng, peaks, torch.cuda.current_stream().cuda_stream)
     # dominant kernel = the tcgen05 GEMM template (84 % of the step, profiles/r1f_launches_bench.csv): its four

@@ -130,10 +130,10 @@ def test_device_resize_matches_pil(engine, crop):
 
 @pytest.mark.gpu
 def test_device_resize_many_images_and_arbitrary_window(engine):
-    """More images than one launch carries (64), and a crop window that is not centred."""
+    """More images than one launch carries (512), and a crop window that is not centred."""
     import torch
     rng = np.random.default_rng(12)
-    arrs = [_img(rng, int(rng.integers(200, 420)), int(rng.integers(200, 420))) for _ in range(150)]
+    arrs = [_img(rng, int(rng.integers(200, 330)), int(rng.integers(200, 330))) for _ in range(530)]
     buf, d = P.pack_rgb(arrs)
     d = d.copy()
     d["new_width"][:3], d["new_height"][:3], d["left"][:3], d["top"][:3] = 300, 260, (0, 76, 31), (36, 0, 17)
@@ -142,6 +142,26 @@ def test_device_resize_many_images_and_arbitrary_window(engine):
         nw, nh, left, top = (int(d[k][i]) for k in ("new_width", "new_height", "left", "top"))
         ref = np.asarray(PIL.Image.fromarray(a).resize((nw, nh), resample=PIL.Image.BICUBIC))[top:top + 224, left:left + 224]
         assert np.array_equal(got[i], ref), f"image {i}"
+
+
+@pytest.mark.gpu
+def test_device_resize_source_ending_mid_word(engine):
+    """The kernel fetches source bytes as aligned 32-bit words; a buffer whose size is not a multiple of 4 must
+    still be read correctly (and never past its end) for the last pixels of the last image."""
+    import torch
+    rng = np.random.default_rng(14)
+    for h, w in [(225, 225), (227, 301), (451, 233)]:
+        a = _img(rng, h, w)
+        assert (h * w * 3) % 4 != 0
+        src = torch.from_numpy(a.reshape(-1).copy()).cuda()            # exactly h*w*3 bytes, no padding
+        d = np.zeros(1, dtype=P.RESIZE_DESC_DTYPE)
+        d[0] = (0, w, h) + P.resize_plan(w, h)
+        # crop windows that touch the right / bottom edge of the resized image
+        nw, nh = int(d["new_width"][0]), int(d["new_height"][0])
+        d["left"][0], d["top"][0] = nw - 224, nh - 224
+        got = engine.resize_crop(src, d).cpu().numpy()[0]
+        ref = np.asarray(PIL.Image.fromarray(a).resize((nw, nh), resample=PIL.Image.BICUBIC))[nh - 224:, nw - 224:]
+        assert np.array_equal(got, ref)
 
 
 @pytest.mark.gpu
