@@ -29,7 +29,7 @@ extern "C" {
 
 #define PLIP_API __attribute__((visibility("default")))
 
-#define PLIP_B200_ABI_VERSION 2
+#define PLIP_B200_ABI_VERSION 3  /* 3: + plip_resize_crop_u8 */
 
 /* Model constants (TF:configuration_clip.py:47-64,97-109,160-161). */
 #define PLIP_IMAGE_SIZE 224

@@ -269,59 +269,70 @@ int resize_filter_host(int in_size, int out_size, int xx, int32_t* k, int k_cap,
   return f.ksize;
 }
 
+// Validates descriptor `idx` and fills the kernel-side plan (strip height, shared memory need).
+static int plan_image(const plip_resize_desc_t& s, long long idx, size_t src_bytes, ResizeImg& o, size_t& need_out) {
+  PLIP_REQUIRE(s.width > 0 && s.height > 0 && s.width <= 65536 && s.height <= 65536,
+               "plip_resize_crop_u8: image %lld has invalid size %dx%d", idx, s.width, s.height);
+  PLIP_REQUIRE(s.offset >= 0 && (uint64_t)s.offset + (uint64_t)s.width * s.height * 3 <= src_bytes,
+               "plip_resize_crop_u8: image %lld (%dx%d at byte %lld) exceeds the %llu-byte source buffer", idx,
+               s.width, s.height, (long long)s.offset, (unsigned long long)src_bytes);
+  PLIP_REQUIRE(s.new_width >= kImage && s.new_height >= kImage && s.new_width <= 65536 && s.new_height <= 65536,
+               "plip_resize_crop_u8: image %lld: resized size %dx%d is smaller than the %dx%d tile", idx,
+               s.new_width, s.new_height, kImage, kImage);
+  PLIP_REQUIRE(s.left >= 0 && s.top >= 0 && s.left + kImage <= s.new_width && s.top + kImage <= s.new_height,
+               "plip_resize_crop_u8: image %lld: crop origin (%d,%d) leaves the %dx%d resized image", idx, s.left,
+               s.top, s.new_width, s.new_height);
+  const int ksh = axis_ksize(s.width, s.new_width), ksv = axis_ksize(s.height, s.new_height);
+  const size_t tb = table_bytes(ksh, ksv);
+  // Strip height: taller strips re-read fewer source rows (adjacent strips overlap by the filter support),
+  // shorter ones need less shared memory and keep more CTAs per SM.  Relative throughput by resident CTAs
+  // measured on B200 (profiles/r1_resize_probe.json); registers cap residency at 5.
+  static const double kThroughput[6] = {0.0, 1.0, 1.12, 1.21, 1.57, 1.70};
+  const double vscale = (double)s.height / (double)s.new_height, fs = vscale < 1.0 ? 1.0 : vscale;
+  int rp = 0, rows = 0;
+  double best = 0.0;
+  for (int cand = kRsRowsPerCta; cand >= 1; cand >>= 1) {
+    const int r = strip_rows_for(s.height, s.new_height, cand);
+    const size_t need = tb + (size_t)(r + kStripPadRows) * kTileRowBytes;
+    if (need > kRsSmemHard) continue;
+    int resident = (int)((size_t)227 * 1024 / (need + 1024));
+    resident = resident > 5 ? 5 : resident;
+    const double reread = ((cand - 1) * vscale + 4.0 * fs + 1.0) / (cand * vscale);
+    const double score = kThroughput[resident] / reread;
+    if (score > best) best = score, rp = cand, rows = r;
+  }
+  PLIP_REQUIRE(rp, "plip_resize_crop_u8: image %lld (%dx%d -> %dx%d) shrinks too much for the on-device "
+               "resize (filter tables need %zu bytes of shared memory); reduce it on the host first",
+               idx, s.width, s.height, s.new_width, s.new_height, tb);
+  o.src_off = s.offset;
+  o.w = s.width, o.h = s.height, o.new_w = s.new_width, o.new_h = s.new_height;
+  o.left = s.left, o.top = s.top, o.rows_per_pass = rp, o.strip_rows = rows;
+  need_out = tb + (size_t)(rows + kStripPadRows) * kTileRowBytes;
+  return 0;
+}
+
 int launch_resize_crop(const uint8_t* src, size_t src_bytes, const plip_resize_desc_t* d, int64_t n, uint8_t* tiles,
                        cudaStream_t st) {
+  PLIP_REQUIRE(reinterpret_cast<uintptr_t>(src) % 4 == 0 && reinterpret_cast<uintptr_t>(tiles) % 4 == 0,
+               "plip_resize_crop_u8: src_dev and tiles_dev must be 4-byte aligned");
+  // every descriptor is checked before anything is launched: a bad one leaves the output untouched
+  {
+    ResizeImg scratch;
+    size_t need;
+    for (int64_t i = 0; i < n; ++i)
+      if (int rc = plan_image(d[i], (long long)i, src_bytes, scratch, need)) return rc;
+  }
   static unsigned long long configured = 0;
   if (first_use_on_device(configured))
     PLIP_CUDA_CHECK(cudaFuncSetAttribute(resize_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kRsSmemHard));
-  PLIP_REQUIRE(reinterpret_cast<uintptr_t>(src) % 4 == 0 && reinterpret_cast<uintptr_t>(tiles) % 4 == 0,
-               "plip_resize_crop_u8: src_dev and tiles_dev must be 4-byte aligned");
   for (int64_t base = 0; base < n; base += kRsBatch) {
     const int cnt = (int)((n - base) < kRsBatch ? (n - base) : kRsBatch);
     static thread_local ResizeBatch b;  // 20 KB: kept off the stack
     size_t smem = 0;
     for (int i = 0; i < cnt; ++i) {
-      const plip_resize_desc_t& s = d[base + i];
-      const long long idx = (long long)(base + i);
-      PLIP_REQUIRE(s.width > 0 && s.height > 0 && s.width <= 65536 && s.height <= 65536,
-                   "plip_resize_crop_u8: image %lld has invalid size %dx%d", idx, s.width, s.height);
-      PLIP_REQUIRE(s.offset >= 0 && (uint64_t)s.offset + (uint64_t)s.width * s.height * 3 <= src_bytes,
-                   "plip_resize_crop_u8: image %lld (%dx%d at byte %lld) exceeds the %llu-byte source buffer", idx,
-                   s.width, s.height, (long long)s.offset, (unsigned long long)src_bytes);
-      PLIP_REQUIRE(s.new_width >= kImage && s.new_height >= kImage && s.new_width <= 65536 && s.new_height <= 65536,
-                   "plip_resize_crop_u8: image %lld: resized size %dx%d is smaller than the %dx%d tile", idx,
-                   s.new_width, s.new_height, kImage, kImage);
-      PLIP_REQUIRE(s.left >= 0 && s.top >= 0 && s.left + kImage <= s.new_width && s.top + kImage <= s.new_height,
-                   "plip_resize_crop_u8: image %lld: crop origin (%d,%d) leaves the %dx%d resized image", idx, s.left,
-                   s.top, s.new_width, s.new_height);
-      const int ksh = axis_ksize(s.width, s.new_width), ksv = axis_ksize(s.height, s.new_height);
-      const size_t tb = table_bytes(ksh, ksv);
-      // Strip height: taller strips re-read fewer source rows (adjacent strips overlap by the filter support),
-      // shorter ones need less shared memory and keep more CTAs per SM.  Relative throughput by resident CTAs
-      // measured on B200 (profiles/r1_resize_probe.json); registers cap residency at 5.
-      static const double kThroughput[6] = {0.0, 1.0, 1.12, 1.21, 1.57, 1.70};
-      const double vscale = (double)s.height / (double)s.new_height, fs = vscale < 1.0 ? 1.0 : vscale;
-      int rp = 0, rows = 0;
-      double best = 0.0;
-      for (int cand = kRsRowsPerCta; cand >= 1; cand >>= 1) {
-        const int r = strip_rows_for(s.height, s.new_height, cand);
-        const size_t need = tb + (size_t)(r + kStripPadRows) * kTileRowBytes;
-        if (need > kRsSmemHard) continue;
-        int resident = (int)((size_t)227 * 1024 / (need + 1024));
-        resident = resident > 5 ? 5 : resident;
-        const double reread = ((cand - 1) * vscale + 4.0 * fs + 1.0) / (cand * vscale);
-        const double score = kThroughput[resident] / reread;
-        if (score > best) best = score, rp = cand, rows = r;
-      }
-      PLIP_REQUIRE(rp, "plip_resize_crop_u8: image %lld (%dx%d -> %dx%d) shrinks too much for the on-device "
-                   "resize (filter tables need %zu bytes of shared memory); reduce it on the host first",
-                   idx, s.width, s.height, s.new_width, s.new_height, tb);
-      ResizeImg& o = b.img[i];
-      o.src_off = s.offset;
-      o.w = s.width, o.h = s.height, o.new_w = s.new_width, o.new_h = s.new_height;
-      o.left = s.left, o.top = s.top, o.rows_per_pass = rp, o.strip_rows = rows;
-      const size_t need = tb + (size_t)(rows + kStripPadRows) * kTileRowBytes;
+      size_t need = 0;
+      if (int rc = plan_image(d[base + i], (long long)(base + i), src_bytes, b.img[i], need)) return rc;
       smem = need > smem ? need : smem;
     }
     PLIP_CUDA_CHECK(launch_pdl(resize_crop_kernel, dim3(kImage / kRsRowsPerCta, cnt), dim3(kRsThreads), smem, st, 1,

@@ -28,7 +28,7 @@ def test_header_symbols_all_exported_and_bound():
 
 def test_abi_version_and_layout_queries():
     L = _lib.lib()
-    assert L.plip_abi_version() == 2
+    assert L.plip_abi_version() == 3
     n = L.plip_weights_num_tensors()
     assert n == 5 + 12 * 10 + 3 + 2 + 12 * 10 + 3
     prev_end = 0
@@ -60,3 +60,52 @@ def test_errors_are_codes_not_exceptions():
     with pytest.raises(RuntimeError, match="blob"):
         _lib.check(rc, "plip_create")
     assert L.plip_destroy(None) == 0
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/plip_b200.h is the boundary a C host binds: it must compile as C99 (no C++ / torch types) and the
+    shared library must link without CUDA or python on the link line."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "host.c"
+    src.write_text('#include "plip_b200.h"\n'
+                   'int main(void) {\n'
+                   '  plip_resize_desc_t d = {0, 1, 1, 224, 224, 0, 0};\n'
+                   '  plip_tensor_info_t ti;\n'
+                   '  if (sizeof d != 32) return 2;\n'
+                   '  if (plip_weights_tensor_info(0, &ti) != 0) return 3;\n'
+                   '  if (plip_destroy(0) != 0) return 4;\n'
+                   '  return plip_abi_version() == PLIP_B200_ABI_VERSION ? 0 : 1;\n'
+                   '}\n')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(str(_lib.LIB_PATH))
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-L", libdir, "-lplip_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_argument_validation_needs_no_gpu():
+    """Bad arguments are rejected with a code + message before any CUDA call."""
+    L = _lib.lib()
+    assert L.plip_similarity(None, 1, None, 1, C.c_float(1.0), 0, 0, None, 1, None) != 0
+    assert "null argument" in _lib.last_error()
+    assert L.plip_l2_normalize(None, 1, 512, None) != 0
+    d = _lib.ResizeDesc(0, 10, 10, 224, 224, 0, 0)
+    assert L.plip_resize_crop_u8(None, 300, C.byref(d), 1, None, None) != 0
+    assert "null argument" in _lib.last_error()
+    buf = (C.c_char * 512)()
+    addr = C.addressof(buf)
+    addr += (-addr) % 4
+    assert L.plip_resize_crop_u8(addr, 300, C.byref(d), 0, addr, None) != 0
+    assert "positive" in _lib.last_error()
+    for bad, msg in [(_lib.ResizeDesc(0, 10, 10, 224, 224, 0, 0), "exceeds"),          # 10x10x3 = 300 > 256
+                     (_lib.ResizeDesc(0, 5, 5, 100, 224, 0, 0), "smaller"),
+                     (_lib.ResizeDesc(0, 5, 5, 224, 224, 0, 3), "crop origin"),
+                     (_lib.ResizeDesc(0, 0, 5, 224, 224, 0, 0), "invalid size")]:
+        assert L.plip_resize_crop_u8(addr, 256, C.byref(bad), 1, addr, None) != 0     # rejected on the host
+        assert msg in _lib.last_error(), _lib.last_error()
+    assert L.plip_resize_crop_u8(addr + 1, 256, C.byref(_lib.ResizeDesc(0, 5, 5, 224, 224, 0, 0)), 1, addr, None) != 0
+    assert "aligned" in _lib.last_error()
