@@ -17,6 +17,9 @@
  *     entry points never synchronise the host.  One handle per device; calls on one handle share a
  *     workspace and are serialised on the device (each call waits, stream-side, for the previous one);
  *     a handle must not be used from two host threads at once.
+ *   - device-pointer entry points launch on the CALLER'S current device: make the handle's device (or, for the
+ *     handle-free functions, the device that owns the buffers) current first, as for any CUDA library call.  The
+ *     *_host entry points select the handle's device themselves.
  */
 #ifndef PLIP_B200_H_
 #define PLIP_B200_H_

@@ -58,9 +58,8 @@ void add_tower(std::vector<Spec>& v, const std::string& pfx, int D, int FF) {
   }
 }
 
-const std::vector<Spec>& specs() {
-  static std::vector<Spec> v;
-  if (!v.empty()) return v;
+std::vector<Spec> build_specs() {
+  std::vector<Spec> v;
   add(v, "vision_model.embeddings.patch_embedding.weight", 1, kVisDim, kPatchK);
   add(v, "vision_model.embeddings.class_embedding", 0, kVisDim, 1);
   add(v, "vision_model.embeddings.position_embedding.weight", 0, kVisSeq, kVisDim);
@@ -82,6 +81,11 @@ const std::vector<Spec>& specs() {
     off += s.numel * (s.dtype == 1 ? 2 : 4);
     off = (off + 255) & ~255ull;
   }
+  return v;
+}
+
+const std::vector<Spec>& specs() {
+  static const std::vector<Spec> v = build_specs();  // C++11: initialised once, thread-safe
   return v;
 }
 
@@ -383,17 +387,19 @@ PLIP_API int plip_create(const void* host_blob, uint64_t nbytes, float logit_sca
   e->device = device;
   e->max_mb = max_micro_batch;
   e->logit_scale_exp = logit_scale_exp;
-  PLIP_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));
   const WsLayout w = ws_layout(max_micro_batch);
   uint8_t* ws = nullptr;
-  if (cudaMalloc(&e->d_blob, nbytes) != cudaSuccess || cudaMalloc(&ws, w.total) != cudaSuccess) {
-    set_last_error("plip_create: cudaMalloc of %llu + %llu bytes failed: %s", (unsigned long long)nbytes,
-                   (unsigned long long)w.total, cudaGetErrorString(cudaGetLastError()));
-    if (e->d_blob) cudaFree(e->d_blob);
-    delete e;
+  cudaError_t ce = cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaMalloc(&e->d_blob, nbytes);
+  if (ce == cudaSuccess) ce = cudaMalloc(&ws, w.total);
+  e->X = reinterpret_cast<float*>(ws);  // workspace base (w.x == 0): what plip_destroy frees
+  if (ce != cudaSuccess) {
+    set_last_error("plip_create: allocating %llu (weights) + %llu (workspace) bytes on device %d failed: %s",
+                   (unsigned long long)nbytes, (unsigned long long)w.total, device, cudaGetErrorString(ce));
+    cudaGetLastError();
+    plip_destroy(e);
     return -1;
   }
-  e->X = reinterpret_cast<float*>(ws + w.x);
   e->Xn = reinterpret_cast<__nv_bfloat16*>(ws + w.xn);
   e->AO = reinterpret_cast<__nv_bfloat16*>(ws + w.ao);
   e->stats = reinterpret_cast<float2*>(ws + w.stats);
@@ -402,12 +408,14 @@ PLIP_API int plip_create(const void* host_blob, uint64_t nbytes, float logit_sca
   e->pooled = reinterpret_cast<__nv_bfloat16*>(ws + w.pooled);
   e->row_idx = reinterpret_cast<int32_t*>(ws + w.rowidx);
   e->kmask = reinterpret_cast<int32_t*>(ws + w.kmask);
-  cudaError_t ce = cudaMemcpy(e->d_blob, host_blob, nbytes, cudaMemcpyHostToDevice);
-  if (ce != cudaSuccess || bind_weights(e) != 0) {
-    if (ce != cudaSuccess) set_last_error("plip_create: weight upload failed: %s", cudaGetErrorString(ce));
-    cudaFree(e->d_blob);
-    cudaFree(ws);
-    delete e;
+  ce = cudaMemcpy(e->d_blob, host_blob, nbytes, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    set_last_error("plip_create: weight upload failed: %s", cudaGetErrorString(ce));
+    plip_destroy(e);
+    return -1;
+  }
+  if (bind_weights(e) != 0) {
+    plip_destroy(e);
     return -1;
   }
   *out = e;
