@@ -12,9 +12,10 @@
 // One CTA produces 32 output rows of one tile (7 CTAs per image).  Its 256 threads first build the 224
 // horizontal filter rows it needs (only the cropped columns) and its 32 vertical ones in shared memory, zero-padded
 // to a multiple of 4 taps.  Then, for `rows_per_pass` output rows at a time, the horizontal pass runs over the
-// source rows those outputs touch — one thread per (row, column), all 3 channels, source bytes fetched as aligned
-// 32-bit words and re-aligned with funnel shifts (4 pixels = 3 words per step, weights as one 16-byte shared load)
-// — into a uint8 shared-memory strip, and the vertical pass runs out of that strip, one thread per 4 output bytes.
+// source rows those outputs touch — one thread per output column walking down the rows, all 3 channels, source
+// bytes fetched as aligned 32-bit words and re-aligned with funnel shifts (4 pixels = 3 words per step; weights in
+// registers for filters of up to 7 taps, else 16-byte shared loads) — into a uint8 shared-memory strip, and the
+// vertical pass runs out of that strip, one thread per 4 output bytes.
 // Source pixels are read once per strip (strips overlap by the filter support; L2 absorbs the re-reads); the
 // roofline is HBM (source bytes + 150,528 tile bytes per image) but the kernel is issue-bound: H_src x 224 x 3 x
 // taps integer MACs per image with ~3 instructions each (profiles/r1_resize_probe.json).
@@ -131,29 +132,43 @@ __device__ __forceinline__ uint32_t src_word(const uint32_t* q, const uint32_t* 
   return w;
 }
 
-// One output pixel of the horizontal pass: 3 channels x `cnt4` taps (a multiple of 4; weights beyond the window
-// are zero).  The window's bytes are fetched as aligned words and re-aligned with a funnel shift, 4 pixels (three
-// words) per step.
+// Four taps of one output pixel of the horizontal pass, all 3 channels: the next 12 source bytes are fetched as
+// aligned words and re-aligned with funnel shifts (`prev` carries the last word over to the next group).
+template <bool GUARD>
+__device__ __forceinline__ void hgroup(const uint32_t*& wp, uint32_t& prev, uint32_t sh, const int4 kk,
+                                       const uint32_t* end_w, const uint8_t* end_b, int& a0, int& a1, int& a2) {
+  const uint32_t w1 = src_word<GUARD>(wp + 1, end_w, end_b), w2 = src_word<GUARD>(wp + 2, end_w, end_b),
+                 w3 = src_word<GUARD>(wp + 3, end_w, end_b);
+  const uint32_t s0 = __funnelshift_r(prev, w1, sh), s1 = __funnelshift_r(w1, w2, sh),
+                 s2 = __funnelshift_r(w2, w3, sh);
+  prev = w3;
+  wp += 3;
+  a0 += byte_of(s0, 0) * kk.x + byte_of(s0, 3) * kk.y + byte_of(s1, 2) * kk.z + byte_of(s2, 1) * kk.w;
+  a1 += byte_of(s0, 1) * kk.x + byte_of(s1, 0) * kk.y + byte_of(s1, 3) * kk.z + byte_of(s2, 2) * kk.w;
+  a2 += byte_of(s0, 2) * kk.x + byte_of(s1, 1) * kk.y + byte_of(s2, 0) * kk.z + byte_of(s2, 3) * kk.w;
+}
+
+// One output pixel: `cnt4` taps (a multiple of 4; weights beyond the window are zero) from shared memory.
 template <bool GUARD>
 __device__ __forceinline__ void hpass_pixel(const uint8_t* p, const int* __restrict__ k, int cnt4,
                                             const uint32_t* end_w, const uint8_t* end_b, int& a0, int& a1, int& a2) {
   const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
   const uint32_t* wp = reinterpret_cast<const uint32_t*>(p - mis);
-  const uint32_t sh = mis * 8;
   uint32_t prev = src_word<GUARD>(wp, end_w, end_b);
   const int4* k4 = reinterpret_cast<const int4*>(k);
-  for (int x = 0; x < cnt4; x += 4) {
-    const uint32_t w1 = src_word<GUARD>(wp + 1, end_w, end_b), w2 = src_word<GUARD>(wp + 2, end_w, end_b),
-                   w3 = src_word<GUARD>(wp + 3, end_w, end_b);
-    const uint32_t s0 = __funnelshift_r(prev, w1, sh), s1 = __funnelshift_r(w1, w2, sh),
-                   s2 = __funnelshift_r(w2, w3, sh);
-    prev = w3;
-    wp += 3;
-    const int4 kk = *k4++;
-    a0 += byte_of(s0, 0) * kk.x + byte_of(s0, 3) * kk.y + byte_of(s1, 2) * kk.z + byte_of(s2, 1) * kk.w;
-    a1 += byte_of(s0, 1) * kk.x + byte_of(s1, 0) * kk.y + byte_of(s1, 3) * kk.z + byte_of(s2, 2) * kk.w;
-    a2 += byte_of(s0, 2) * kk.x + byte_of(s1, 1) * kk.y + byte_of(s2, 0) * kk.z + byte_of(s2, 3) * kk.w;
-  }
+  for (int x = 0; x < cnt4; x += 4) hgroup<GUARD>(wp, prev, mis * 8, *k4++, end_w, end_b, a0, a1, a2);
+}
+
+// One output pixel with exactly 8 (zero-padded) taps held in registers: every filter up to 7 taps, i.e. any
+// scale factor <= 1.5 and all upscaling.
+template <bool GUARD>
+__device__ __forceinline__ void hpass_pixel8(const uint8_t* p, const int4 k0, const int4 k1, const uint32_t* end_w,
+                                             const uint8_t* end_b, int& a0, int& a1, int& a2) {
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(p - mis);
+  uint32_t prev = src_word<GUARD>(wp, end_w, end_b);
+  hgroup<GUARD>(wp, prev, mis * 8, k0, end_w, end_b, a0, a1, a2);
+  hgroup<GUARD>(wp, prev, mis * 8, k1, end_w, end_b, a0, a1, a2);
 }
 
 __global__ void __launch_bounds__(kRsThreads) resize_crop_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes,
@@ -202,22 +217,39 @@ __global__ void __launch_bounds__(kRsThreads) resize_crop_kernel(const uint8_t* 
     const int s1 = bv[2 * (sub + rp - 1)] + bv[2 * (sub + rp - 1) + 1];
     const int nrows = s1 - s0;
     if (nrows > im.strip_rows) __trap();  // host sizing bug: never expected
-    // horizontal pass: strip[r][xx][0..2] for the source rows [s0, s1); one thread per (row, column)
-    for (int idx = t; idx < nrows * kImage; idx += kRsThreads) {
-      const int r = idx / kImage, xx = idx - r * kImage;
-      const int xmin = bh[2 * xx], cnt4 = (bh[2 * xx + 1] + 3) & ~3;
-      const uint8_t* p = img + (int64_t)(s0 + r) * src_row_bytes + (int64_t)xmin * 3;
-      const int* k = kh + xx * ksh4;
-      int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-      // words read: [p & ~3, ... + 3*cnt4 + 4) bytes; only the very end of the source buffer needs the guard
-      if (p + 3 * cnt4 + 8 <= reinterpret_cast<const uint8_t*>(end_w))
-        hpass_pixel<false>(p, k, cnt4, end_w, end_b, a0, a1, a2);
-      else
-        hpass_pixel<true>(p, k, cnt4, end_w, end_b, a0, a1, a2);
-      uint8_t* d = strip + r * kTileRowBytes + xx * 3;
-      d[0] = (uint8_t)clip8(a0);
-      d[1] = (uint8_t)clip8(a1);
-      d[2] = (uint8_t)clip8(a2);
+    // horizontal pass: strip[r][xx][0..2] for the source rows [s0, s1).  Thread t owns output column t (window,
+    // weights and pointers are then loop invariants) and walks down the rows; threads 224..255 sit this out.
+    if (t < kImage) {
+      const uint8_t* p = img + (int64_t)s0 * src_row_bytes + (int64_t)bh[2 * t] * 3;
+      const uint8_t* lim = reinterpret_cast<const uint8_t*>(end_w);
+      uint8_t* d = strip + t * 3;
+      if (ksh4 == 8) {
+        const int4 k0 = reinterpret_cast<const int4*>(kh + t * 8)[0], k1 = reinterpret_cast<const int4*>(kh + t * 8)[1];
+        for (int r = 0; r < nrows; ++r, p += src_row_bytes, d += kTileRowBytes) {
+          int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+          // words read: [p & ~3, ... + 28) bytes; only the very end of the source buffer needs the guard
+          if (p + 32 <= lim)
+            hpass_pixel8<false>(p, k0, k1, end_w, end_b, a0, a1, a2);
+          else
+            hpass_pixel8<true>(p, k0, k1, end_w, end_b, a0, a1, a2);
+          d[0] = (uint8_t)clip8(a0);
+          d[1] = (uint8_t)clip8(a1);
+          d[2] = (uint8_t)clip8(a2);
+        }
+      } else {
+        const int cnt4 = (bh[2 * t + 1] + 3) & ~3;
+        const int* k = kh + t * ksh4;
+        for (int r = 0; r < nrows; ++r, p += src_row_bytes, d += kTileRowBytes) {
+          int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+          if (p + 3 * cnt4 + 8 <= lim)  // words read: [p & ~3, ... + 3*cnt4 + 4) bytes
+            hpass_pixel<false>(p, k, cnt4, end_w, end_b, a0, a1, a2);
+          else
+            hpass_pixel<true>(p, k, cnt4, end_w, end_b, a0, a1, a2);
+          d[0] = (uint8_t)clip8(a0);
+          d[1] = (uint8_t)clip8(a1);
+          d[2] = (uint8_t)clip8(a2);
+        }
+      }
     }
     __syncthreads();
     // vertical pass: rp output rows out of the strip; one thread per 4 output bytes
