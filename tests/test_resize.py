@@ -3,6 +3,8 @@
 The reference resizes with PIL on the host (``plip.py:35`` through CLIPProcessor; ``reproducibility/embedders/
 transform.py:45-52`` through torchvision on PIL images).  Integer work: every comparison here is bit-exact."""
 import ctypes as C
+import hashlib
+import os
 
 import numpy as np
 import PIL.Image
@@ -22,6 +24,36 @@ def _img(rng, h, w, kind="noise"):
     yy, xx = np.mgrid[0:h, 0:w]
     base = ((xx * 7 + yy * 3) % 256).astype(np.uint8)           # sharp diagonal stripes: exercises the clamp
     return np.stack([base, 255 - base, ((xx // 8 + yy // 8) % 2 * 255).astype(np.uint8)], axis=-1)
+
+
+def _golden():
+    import importlib.util
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "resize_golden.npz"))
+    spec = importlib.util.spec_from_file_location("make_resize_golden",
+                                                  os.path.join(os.path.dirname(__file__), "golden", "make_resize_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cases = [(int(h), int(w), int(seed), str(k), str(c))
+             for (h, w, seed), k, c in zip(g["cases"], g["kinds"], g["crops"])]
+    return mod.make_image, cases, [str(x) for x in g["sha256"]], g["patches"]
+
+
+def _sha(tile):
+    return hashlib.sha256(np.ascontiguousarray(tile).tobytes()).hexdigest()
+
+
+def test_oracle_and_host_path_match_committed_golden_tiles():
+    """Frozen outputs of the reference's own pipelines (torchvision transform / transformers PIL processor,
+    tests/golden/make_resize_golden.py): the oracle and the PIL host route must reproduce them byte for byte."""
+    make_image, cases, shas, patches = _golden()
+    assert len(cases) >= 8
+    for (h, w, seed, kind, crop), sha, patch in zip(cases, shas, patches):
+        a = make_image(h, w, seed, kind)
+        nw, nh, left, top = P.resize_plan(w, h, crop=crop)
+        tile = R.resize_crop_u8(a, nw, nh, left, top)
+        assert np.array_equal(tile[:24, :24], patch) and _sha(tile) == sha, (h, w, crop)
+        host = P.to_uint8_tiles([a], crop=crop)[0]
+        assert _sha(host) == sha, (h, w, crop)
 
 
 def _pil_tile(a, crop):
@@ -126,6 +158,18 @@ def test_device_resize_matches_pil(engine, crop):
     # the oracle agrees too (one mid-size case; the rest is covered on the CPU tier)
     nw, nh, left, top = P.resize_plan(500, 300, crop=crop)
     assert np.array_equal(got[1], R.resize_crop_u8(arrs[1], nw, nh, left, top))
+
+
+@pytest.mark.gpu
+def test_device_resize_matches_committed_golden_tiles(engine):
+    make_image, cases, shas, patches = _golden()
+    for crop in ("floor", "round"):
+        sel = [i for i, c in enumerate(cases) if c[4] == crop]
+        arrs = [make_image(*cases[i][:4]) for i in sel]
+        buf, d = P.pack_rgb(arrs, crop=crop)
+        got = engine.resize_crop(buf.cuda(), d).cpu().numpy()
+        for j, i in enumerate(sel):
+            assert np.array_equal(got[j][:24, :24], patches[i]) and _sha(got[j]) == shas[i], cases[i]
 
 
 @pytest.mark.gpu
