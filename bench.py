@@ -412,6 +412,19 @@ def run_ours(args):
         pass
     if not args.no_context:
         towers["stock_pytorch_bf16_same_gpu"] = stock_pytorch_context(sd, dev)
+    try:  # BASELINE.json configs[2] shape: 4096 images (4 micro-batches of 1024) x 1024 captions -> logits [4096,1024]
+        def cfg3_step():
+            txt3 = eng.encode_text(ids[0], normalize=True)
+            return [eng.similarity(eng.encode_images(px[j % nsets], normalize=True), txt3, normalize_image=False,
+                                   normalize_text=False) for j in range(4)]
+        ms_c3 = tower(cfg3_step)
+        flop_c3 = 4 * PAIRS * FLOP_IMG + PAIRS * FLOP_TXT + 2.0 * 4 * PAIRS * PAIRS * 512
+        towers["cfg3_4096_images_x_1024_captions"] = {
+            "ms": ms_c3, "images_per_s": 4 * PAIRS / ms_c3 * 1e3, "captions_per_s": PAIRS / ms_c3 * 1e3,
+            "tflops": flop_c3 / ms_c3 / 1e9, "note": "pairs/s as N_img / t with N_txt / N_img = 1/4 (SURVEY.md §8d); "
+            "the headline value uses the symmetric 1024 x 1024 step"}
+    except Exception as exc:  # noqa: BLE001 - context only
+        towers["cfg3_4096_images_x_1024_captions"] = {"error": str(exc)}
     try:  # image preparation on the device: 1024 decoded 256x256 RGB images -> 224x224 tiles
         from plip_b200 import preprocess as P
         rs_rng = np.random.default_rng(7)
