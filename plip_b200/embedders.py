@@ -19,7 +19,7 @@ import torch
 
 from .modeling import PlipCLIPModel
 from .tokenizer import find_tokenizer
-from .preprocess import SIZE, chunks, decode_rgb, pack_rgb, to_uint8_tiles
+from .preprocess import SIZE, chunks, decode_rgb, device_resizable, pack_rgb, to_uint8_tiles
 
 
 class AbstractEmbedder(ABC):
@@ -74,6 +74,9 @@ class CLIPEmbedder(AbstractEmbedder):
                 arrays = decode_rgb(chunk, int(num_workers))
                 if all(a.shape == (SIZE, SIZE, 3) for a in arrays):
                     outs.append(eng.encode_images_host(np.stack(arrays, axis=0), normalize=True))
+                elif not all(device_resizable(a.shape[1], a.shape[0]) for a in arrays):  # too large: PIL
+                    outs.append(eng.encode_images_host(to_uint8_tiles(arrays, int(num_workers), crop="round"),
+                                                       normalize=True))
                 else:  # Pillow-exact bicubic resize + crop on the device
                     buf, descs = pack_rgb(arrays, crop="round", pinned=True)
                     tiles = eng.resize_crop(buf.to(eng.device, non_blocking=True), descs)

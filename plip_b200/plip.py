@@ -23,7 +23,7 @@ from tqdm import tqdm
 
 from .modeling import PlipCLIPModel
 from .tokenizer import find_tokenizer
-from .preprocess import SIZE, chunks, decode_rgb, pack_rgb, to_uint8_tiles
+from .preprocess import SIZE, chunks, decode_rgb, device_resizable, pack_rgb, to_uint8_tiles
 
 
 class PLIP:
@@ -75,6 +75,7 @@ class PLIP:
             raise ValueError("need at least one array to stack")  # np.stack([]) in the reference
         eng = self.model.engine
         flush = max(int(batch_size), eng.max_micro_batch)
+        flush_bytes = 1 << 30            # decoded pixels held on the host (and uploaded at once) per flush
         out = np.empty((len(images), 512), dtype=np.float32)
         pending: List[np.ndarray] = []   # decoded RGB arrays, any size
         done = 0
@@ -86,12 +87,12 @@ class PLIP:
                 return
             if all(a.shape == (SIZE, SIZE, 3) for a in pending):
                 res = eng.encode_images_host(np.stack(pending, axis=0)).numpy()
-            elif self.device_resize:
+            elif self.device_resize and all(device_resizable(a.shape[1], a.shape[0]) for a in pending):
                 # upload the decoded images once; Pillow-exact bicubic resize + centre crop on the device
                 buf, descs = pack_rgb(pending, crop="floor", pinned=True)
                 tiles = eng.resize_crop(buf.to(eng.device, non_blocking=True), descs)
                 res = eng.encode_images(tiles).cpu().numpy()
-            else:
+            else:  # PIL on the host (device_resize=False, or an image shrinks too much for the device kernel)
                 res = eng.encode_images_host(to_uint8_tiles(pending, self.num_workers)).numpy()
             out[done:done + len(pending)] = res
             done += len(pending)
@@ -99,7 +100,7 @@ class PLIP:
 
         for chunk in chunks(images, int(batch_size)):
             pending.extend(decode_rgb(chunk, self.num_workers))
-            if len(pending) >= flush:
+            if len(pending) >= flush or sum(a.nbytes for a in pending) >= flush_bytes:
                 _flush()
             pbar.update(1)
         _flush()

@@ -67,6 +67,24 @@ RESIZE_DESC_DTYPE = np.dtype([("offset", "<i8"), ("width", "<i4"), ("height", "<
                               ("new_height", "<i4"), ("left", "<i4"), ("top", "<i4")])
 
 
+def device_resizable(w: int, h: int, size: int = SIZE) -> bool:
+    """Whether ``plip_resize_crop_u8`` takes a ``w x h`` image: its filter banks (224 horizontal + 32 vertical rows of
+    ``2*ceil(2*scale)+1`` taps, padded to 4) plus one output row's strip of source rows must fit 200 KB of shared
+    memory — shortest edges up to ~6,000 px at ordinary aspect ratios.  Larger images go through PIL."""
+    import math
+    nw, nh, _, _ = resize_plan(w, h, size)
+    if min(w, h) < 1 or max(w, h) > 65536 or max(nw, nh) > 65536:
+        return False
+
+    def taps4(i, o):
+        return (2 * math.ceil(2.0 * max(i / o, 1.0)) + 1 + 3) // 4 * 4
+
+    vs = h / nh
+    tables = (size * taps4(w, nw) + 32 * taps4(h, nh) + 2 * (size + 32)) * 4
+    strip_rows = min(h, math.ceil(4.0 * max(vs, 1.0)) + 3) + 3
+    return tables + strip_rows * size * 3 <= 200 * 1024
+
+
 def pack_rgb(arrays: Sequence[np.ndarray], crop: str = "floor", pinned: bool = False):
     """Concatenate ``[h,w,3] uint8`` arrays into one byte buffer + their resize descriptors.
 

@@ -139,6 +139,80 @@ def test_library_filter_rows_match_oracle(in_size, out_size):
     assert L.plip_dbg_resize_filter(in_size, out_size, out_size, C.addressof(buf), ks, C.byref(xmin), C.byref(cnt)) == -2
 
 
+def test_device_resizable_predicate_matches_library_validation():
+    """``preprocess.device_resizable`` (used to route oversized images to PIL) against the library's own check.
+    On a CPU-only box the call stops at the first CUDA call, after descriptor validation; never run this where a
+    GPU is present (the pointers are fake)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("validation-only probe: needs a box without a GPU")
+    from plip_b200._lib import ResizeDesc, last_error, lib
+    L = lib()
+    sizes = [(256, 256), (1000, 1000), (4000, 3000), (3000, 5000), (6000, 6000), (6500, 6500), (7000, 7000), (8000, 8000),
+             (12000, 9000), (8, 60000), (60000, 8), (20000, 300), (300, 20000), (65536, 224), (224, 65536), (5000, 7000)]
+    seen = set()
+    for w, h in sizes:
+        nw, nh, left, top = P.resize_plan(w, h)
+        d = ResizeDesc(0, w, h, nw, nh, left, top)
+        assert L.plip_resize_crop_u8(4096, 1 << 40, C.byref(d), 1, 4096, None) != 0
+        lib_ok = "shrinks too much" not in last_error() and "invalid size" not in last_error() \
+            and "smaller than" not in last_error()
+        assert lib_ok == P.device_resizable(w, h), (w, h, last_error())
+        seen.add(lib_ok)
+    assert seen == {True, False}
+
+
+def test_plip_encode_images_routes_oversized_images_to_pil():
+    """Flush routing of ``PLIP.encode_images`` with a stub engine: all-224 batches go straight to the host path,
+    resizable batches to the device kernel, batches holding an image the kernel cannot take to PIL."""
+    import torch
+    from plip_b200.plip import PLIP
+
+    class StubEngine:
+        max_micro_batch, device = 4, "cpu"
+
+        def __init__(self):
+            self.calls = []
+
+        def encode_images_host(self, tiles, normalize=False):
+            self.calls.append(("host", tuple(tiles.shape)))
+            return torch.zeros(tiles.shape[0], 512)
+
+        def resize_crop(self, src, descs):
+            self.calls.append(("device_resize", len(descs)))
+            return torch.zeros(len(descs), 224, 224, 3, dtype=torch.uint8)
+
+        def encode_images(self, tiles, normalize=False):
+            self.calls.append(("device", tuple(tiles.shape)))
+            return torch.zeros(tiles.shape[0], 512)
+
+    class StubModel:
+        engine = StubEngine()
+
+    plip = PLIP.__new__(PLIP)
+    plip.model, plip.num_workers, plip.device_resize = StubModel(), 0, True
+    rng = np.random.default_rng(0)
+    import plip_b200.plip as mod
+    real_pack = mod.pack_rgb
+    mod.pack_rgb = lambda arrs, crop="floor", pinned=False: real_pack(arrs, crop=crop, pinned=False)   # no CUDA here
+    try:
+        tiles224 = [_img(rng, 224, 224) for _ in range(4)]
+        mixed = [_img(rng, 300, 260), _img(rng, 224, 224), _img(rng, 240, 500), _img(rng, 224, 224)]
+        out = plip.encode_images(tiles224 + mixed, batch_size=2)
+        assert out.shape == (8, 512)
+        assert StubModel.engine.calls == [("host", (4, 224, 224, 3)), ("device_resize", 4), ("device", (4, 224, 224, 3))]
+        StubModel.engine.calls.clear()
+        assert not P.device_resizable(8, 9000)
+        plip.encode_images([np.zeros((9000, 8, 3), np.uint8), tiles224[0]], batch_size=2)
+        assert StubModel.engine.calls == [("host", (2, 224, 224, 3))]               # PIL route, then the host path
+        StubModel.engine.calls.clear()
+        plip.device_resize = False
+        plip.encode_images(mixed, batch_size=4)
+        assert StubModel.engine.calls == [("host", (4, 224, 224, 3))]
+    finally:
+        mod.pack_rgb = real_pack
+
+
 # ---- GPU ---------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("crop", ["floor", "round"])
