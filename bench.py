@@ -170,7 +170,6 @@ def cpu_baseline_sample():
 
 def kernel_rooflines(eng, peaks, stream):
     """Time the layer GEMM shapes of the vision tower alone (CUDA events on the launch stream)."""
-    import ctypes as C
     from plip_b200._lib import check
     L = eng._L
     M = PAIRS * 50

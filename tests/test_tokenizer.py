@@ -8,8 +8,7 @@ import json
 import numpy as np
 import pytest
 
-from plip_b200.tokenizer import (BOS_TOKEN, EOS_TOKEN, ClipTokenizer, _PATTERN, base_vocab, bytes_to_unicode,
-                                 find_tokenizer)
+from plip_b200.tokenizer import ClipTokenizer, _PATTERN, base_vocab, bytes_to_unicode, find_tokenizer
 
 CORPUS = """an h&e image patch of colorectal adenocarcinoma epithelium tumor stroma lymphocytes mucosa debris adipose
 tissue normal colon mucosa smooth muscle cancer-associated stroma benign malignant glands nuclei pleomorphism mitotic

@@ -29,7 +29,6 @@ CASES = [
 
 
 def run_case(cg, bn, epi, M, N, K):
-    import ctypes as C
     import torch
     from plip_b200._lib import lib, check
     L = lib(strict=False)
