@@ -159,7 +159,10 @@ PLIP_API int plip_resize_crop_u8(const void* src_dev, uint64_t src_bytes, const 
 /* pixels_host / ids_host / out_host are host pointers (pinned or pageable).  The call stages
  * micro-batches through pinned buffers on two streams (H2D overlapped with compute), writes the
  * float32 [n,512] result to out_host and returns after the last D2H completed.
- * plip_encode_text_host scans the ids for the longest caption and uses plip_encode_text_prefix. */
+ * plip_encode_text_host scans the ids for the caption lengths (first eos) and uses plip_encode_text_prefix: one
+ * pass up to the longest caption, or — for large batches of mixed lengths — the captions sorted by length and
+ * processed in up to 8 length buckets, each only up to its own longest caption (results are returned in the
+ * caller's order). */
 PLIP_API int plip_encode_images_host(plip_engine_t* e, const void* pixels_host, int pixel_format, int64_t n,
                                      float* out_host, int normalize);
 PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int ids_dtype,
@@ -178,6 +181,12 @@ PLIP_API int plip_dbg_gemm(const void* A_bf16, int lda, const void* W_bf16, int 
  * kernel runs).  Returns the filter bank width ksize (or -ksize if k_cap is too small). */
 PLIP_API int plip_dbg_resize_filter(int in_size, int out_size, int xx, int32_t* k_host, int k_cap, int* xmin,
                                     int* count);
+/* Host-only: the length-bucket plan plip_encode_text_host uses (lens = first-eos position + 1 per caption).
+ * perm_host[i] = original index of the caption at sorted position i (may be NULL); bucket k covers sorted positions
+ * [bucket_start[k], bucket_start[k+1]) and is processed with prefix bucket_prefix[k].  Arrays hold cap+1 / cap
+ * entries (cap <= 8).  Returns the number of buckets. */
+PLIP_API int plip_dbg_text_bucket_plan(const int32_t* lens_host, int64_t n, int seq_len, int32_t* perm_host,
+                                       int32_t* bucket_start_host, int32_t* bucket_prefix_host, int cap);
 PLIP_API int plip_dbg_rowstats_cast(const float* x, int64_t rows, int dim, void* xb_bf16, float* stats, void* stream);
 PLIP_API int plip_dbg_layernorm(const float* x, int64_t rows, int dim, int64_t in_row_stride,
                                 const float* gamma, const float* beta, float* out_f32, void* out_bf16,

@@ -326,6 +326,70 @@ int grow_dev(void** p, size_t* have, size_t want) {
   return 0;
 }
 
+// Length-bucketed text batches.  The pooled output of a caption depends only on its positions up to
+// the first EOS, so captions sorted by that length can be processed bucket by bucket, each bucket only up to its own
+// longest caption.  Buckets are chosen by dynamic programming over the (<= 77) distinct lengths: cost of a bucket
+// = max(captions x prefix, kMinBucketRows) + kBucketOverheadRows token rows — a GEMM needs ~8k rows to fill the
+// 148 SMs once, and a 66-launch pass costs about as much as 2k token rows — so small or uniform batches stay in
+// one bucket.  perm[i] = original index of the caption at sorted position i (stable); bucket k covers sorted
+// positions [start[k], start[k+1]) and is processed with prefix[k].  Returns the number of buckets.
+constexpr long long kMinBucketRows = 8192, kBucketOverheadRows = 2048;
+constexpr int kMaxTextBuckets = 8;
+
+int plan_text_buckets(const int32_t* lens, int64_t n, int seq_len, int32_t* perm, int32_t* start, int32_t* prefix,
+                      int cap) {
+  std::vector<int64_t> upto(seq_len + 1, 0);  // upto[L] = captions with length <= L
+  for (int64_t i = 0; i < n; ++i) {
+    const int L = lens[i] < 1 ? 1 : (lens[i] > seq_len ? seq_len : lens[i]);
+    ++upto[L];
+  }
+  std::vector<int64_t> first(seq_len + 2, 0);  // counting sort offsets
+  for (int L = 1; L <= seq_len; ++L) first[L + 1] = first[L] + upto[L];
+  if (perm) {
+    std::vector<int64_t> cur(first.begin(), first.end());
+    for (int64_t i = 0; i < n; ++i) {
+      const int L = lens[i] < 1 ? 1 : (lens[i] > seq_len ? seq_len : lens[i]);
+      perm[cur[L]++] = (int32_t)i;
+    }
+  }
+  std::vector<int> ends;  // lengths that occur: the only sensible bucket ends
+  for (int L = 1; L <= seq_len; ++L)
+    if (upto[L]) ends.push_back(L);
+  for (int L = 1; L <= seq_len; ++L) upto[L] += upto[L - 1];
+  const int m = (int)ends.size();
+  const int kb = cap < kMaxTextBuckets ? cap : kMaxTextBuckets;
+  // f[b][j]: cheapest cover of the captions up to length ends[j] with exactly b+1 buckets
+  const long long INF = 1LL << 62;
+  std::vector<std::vector<long long>> f(kb, std::vector<long long>(m, INF));
+  std::vector<std::vector<int>> from(kb, std::vector<int>(m, -1));
+  auto cost = [&](int jlo, int jhi) {  // bucket holding lengths ends[jlo..jhi]
+    const long long cnt = upto[ends[jhi]] - (jlo ? upto[ends[jlo - 1]] : 0);
+    const long long rows = cnt * ends[jhi];
+    return (rows < kMinBucketRows ? kMinBucketRows : rows) + kBucketOverheadRows;
+  };
+  for (int j = 0; j < m; ++j) f[0][j] = cost(0, j);
+  for (int b = 1; b < kb; ++b)
+    for (int j = b; j < m; ++j)
+      for (int i = b - 1; i < j; ++i)
+        if (f[b - 1][i] < INF) {
+          const long long c = f[b - 1][i] + cost(i + 1, j);
+          if (c < f[b][j]) f[b][j] = c, from[b][j] = i;
+        }
+  int best_b = 0;
+  for (int b = 1; b < kb; ++b)
+    if (m > b && f[b][m - 1] < f[best_b][m - 1]) best_b = b;
+  const int nb = best_b + 1;
+  int j = m - 1;
+  for (int b = best_b; b >= 0; --b) {
+    prefix[b] = ends[j];
+    const int i = b ? from[b][j] : -1;
+    start[b] = (int32_t)(i >= 0 ? upto[ends[i]] : 0);
+    j = i;
+  }
+  start[nb] = (int32_t)n;
+  return nb;
+}
+
 bool is_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -601,25 +665,69 @@ PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int i
   if (int rc = grow_dev(reinterpret_cast<void**>(&e->d_out), &e->d_out_bytes, (size_t)n * kProj * 4)) return rc;
   uint8_t* d_ids = static_cast<uint8_t*>(e->d_aux);
   uint8_t* d_mask = attention_mask_host ? d_ids + ib_al : nullptr;
-  PLIP_CUDA_CHECK(cudaMemcpyAsync(d_ids, ids_host, ib, cudaMemcpyHostToDevice, e->s_compute));
-  if (d_mask) PLIP_CUDA_CHECK(cudaMemcpyAsync(d_mask, attention_mask_host, ib, cudaMemcpyHostToDevice, e->s_compute));
-  // Longest caption (first EOS position + 1) scanned on the host: rows after the first EOS cannot influence
-  // the pooled output (causal attention), so only that prefix of every row is processed.
-  int prefix = 1;
-  for (int64_t b = 0; b < n && prefix < seq_len; ++b) {
+  // Caption lengths (first EOS position + 1) scanned on the host: rows after the first EOS cannot influence the
+  // pooled output (causal attention), so only that prefix of every row is processed — per length bucket when
+  // the batch is large and its lengths differ enough to pay for extra passes (plan_text_buckets).
+  PLIP_REQUIRE(n <= 0x7fffffff, "plip_encode_text_host: n too large");
+  std::vector<int32_t> lens((size_t)n);
+  for (int64_t b = 0; b < n; ++b) {
     int len = seq_len;
     for (int t = 0; t < seq_len; ++t) {
       const long long id = ids_dtype == PLIP_IDS_I64 ? static_cast<const long long*>(ids_host)[b * seq_len + t]
                                                      : (long long)static_cast<const int*>(ids_host)[b * seq_len + t];
       if (id == kEosId) { len = t + 1; break; }
     }
-    if (len > prefix) prefix = len;
+    lens[(size_t)b] = len;
   }
-  if (int rc = plip_encode_text_prefix(e, d_ids, ids_dtype, d_mask, n, seq_len, prefix, e->d_out, normalize,
-                                       e->s_compute)) return rc;
-  PLIP_CUDA_CHECK(cudaMemcpyAsync(out_host, e->d_out, (size_t)n * kProj * 4, cudaMemcpyDeviceToHost, e->s_compute));
+  std::vector<int32_t> perm((size_t)n);
+  int32_t start[kMaxTextBuckets + 1], prefix[kMaxTextBuckets];
+  const int nb = plan_text_buckets(lens.data(), n, seq_len, perm.data(), start, prefix, kMaxTextBuckets);
+  if (nb == 1) {
+    PLIP_CUDA_CHECK(cudaMemcpyAsync(d_ids, ids_host, ib, cudaMemcpyHostToDevice, e->s_compute));
+    if (d_mask) PLIP_CUDA_CHECK(cudaMemcpyAsync(d_mask, attention_mask_host, ib, cudaMemcpyHostToDevice, e->s_compute));
+    if (int rc = plip_encode_text_prefix(e, d_ids, ids_dtype, d_mask, n, seq_len, prefix[0], e->d_out, normalize,
+                                         e->s_compute)) return rc;
+    PLIP_CUDA_CHECK(cudaMemcpyAsync(out_host, e->d_out, (size_t)n * kProj * 4, cudaMemcpyDeviceToHost, e->s_compute));
+    PLIP_CUDA_CHECK(cudaStreamSynchronize(e->s_compute));
+    return 0;
+  }
+  // several buckets: upload the rows sorted by length, run each bucket with its own prefix, un-permute on the host
+  const size_t row_bytes = (size_t)seq_len * isz;
+  std::vector<uint8_t> sorted(ib);
+  for (int64_t i = 0; i < n; ++i)
+    memcpy(sorted.data() + (size_t)i * row_bytes, static_cast<const uint8_t*>(ids_host) + (size_t)perm[(size_t)i] * row_bytes,
+           row_bytes);
+  PLIP_CUDA_CHECK(cudaMemcpyAsync(d_ids, sorted.data(), ib, cudaMemcpyHostToDevice, e->s_compute));
+  PLIP_CUDA_CHECK(cudaStreamSynchronize(e->s_compute));  // `sorted` is reused for the mask
+  if (d_mask) {
+    for (int64_t i = 0; i < n; ++i)
+      memcpy(sorted.data() + (size_t)i * row_bytes,
+             static_cast<const uint8_t*>(attention_mask_host) + (size_t)perm[(size_t)i] * row_bytes, row_bytes);
+    PLIP_CUDA_CHECK(cudaMemcpyAsync(d_mask, sorted.data(), ib, cudaMemcpyHostToDevice, e->s_compute));
+    PLIP_CUDA_CHECK(cudaStreamSynchronize(e->s_compute));
+  }
+  for (int k = 0; k < nb; ++k) {
+    const int64_t r0 = start[k], cnt = start[k + 1] - start[k];
+    if (cnt <= 0) continue;
+    if (int rc = plip_encode_text_prefix(e, d_ids + (size_t)r0 * row_bytes, ids_dtype,
+                                         d_mask ? d_mask + (size_t)r0 * row_bytes : nullptr, cnt, seq_len, prefix[k],
+                                         e->d_out + r0 * kProj, normalize, e->s_compute)) return rc;
+  }
+  std::vector<float> tmp((size_t)n * kProj);
+  PLIP_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), e->d_out, (size_t)n * kProj * 4, cudaMemcpyDeviceToHost, e->s_compute));
   PLIP_CUDA_CHECK(cudaStreamSynchronize(e->s_compute));
+  for (int64_t i = 0; i < n; ++i)
+    memcpy(out_host + (size_t)perm[(size_t)i] * kProj, tmp.data() + (size_t)i * kProj, (size_t)kProj * 4);
   return 0;
+}
+
+PLIP_API int plip_dbg_text_bucket_plan(const int32_t* lens_host, int64_t n, int seq_len, int32_t* perm_host,
+                                       int32_t* bucket_start_host, int32_t* bucket_prefix_host, int cap) {
+  if (!lens_host || !bucket_start_host || !bucket_prefix_host || n <= 0 || seq_len < 1 || seq_len > kTxtSeq || cap < 1) {
+    set_last_error("plip_dbg_text_bucket_plan: bad argument");
+    return -2;
+  }
+  return plan_text_buckets(lens_host, n, seq_len, perm_host, bucket_start_host, bucket_prefix_host, cap);
 }
 
 // ---- per-kernel test hooks ------------------------------------------------------------------------
