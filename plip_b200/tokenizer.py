@@ -33,8 +33,13 @@ BOS_TOKEN = "<|startoftext|>"
 EOS_TOKEN = "<|endoftext|>"
 CONTEXT_LENGTH = 77
 
+# OpenAI's simple_tokenizer runs on Python's `regex` (\s = str.isspace(): includes the separators U+001C..U+001F);
+# transformers' CLIPTokenizer runs on the Rust regex crate (\s = Unicode White_Space, which excludes them).
 _PATTERN = re.compile(
     r"""<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""", re.IGNORECASE)
+_PATTERN_HF = re.compile(
+    r"""<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\p{White_Space}\p{L}\p{N}]+""")
+_WS_HF = re.compile(r"\p{White_Space}+")
 
 
 @lru_cache()
@@ -57,11 +62,13 @@ def base_vocab() -> List[str]:
     return v + [s + "</w>" for s in v]
 
 
-def _clean(text: str, unescape_html: bool) -> str:
-    if unescape_html:   # OpenAI basic_clean (minus ftfy, which is not installed); transformers' normaliser skips it
+def _clean(text: str, openai: bool) -> str:
+    if openai:   # basic_clean (minus ftfy, which is not installed) + whitespace_clean + lower
         text = html.unescape(html.unescape(text)).strip()
-    text = unicodedata.normalize("NFC", text)
-    return re.sub(r"\s+", " ", text).strip().lower()
+        return re.sub(r"\s+", " ", text).strip().lower()
+    # transformers: normalizers.Sequence([NFC(), Replace(Regex(r"\s+"), " "), Lowercase()]).  `tokenizers` lowercases
+    # character by character, i.e. without str.lower()'s context rule for a word-final capital sigma.
+    return "".join(c.lower() for c in _WS_HF.sub(" ", unicodedata.normalize("NFC", text)))
 
 
 class ClipTokenizer:
@@ -144,10 +151,11 @@ class ClipTokenizer:
         self._cache[token] = word
         return word
 
-    def encode(self, text: str, unescape_html: bool = False) -> List[int]:
-        """Caption -> token ids, without the start / end tokens."""
+    def encode(self, text: str, openai: bool = False) -> List[int]:
+        """Caption -> token ids, without the start / end tokens.  ``openai`` selects ``clip.tokenize``'s text
+        cleaning and whitespace definition instead of ``transformers.CLIPTokenizer``'s."""
         ids: List[int] = []
-        for tok in _PATTERN.findall(_clean(text, unescape_html)):
+        for tok in (_PATTERN if openai else _PATTERN_HF).findall(_clean(text, openai)):
             if tok in (BOS_TOKEN, EOS_TOKEN):
                 ids.append(self.encoder[tok])
                 continue
@@ -169,7 +177,7 @@ class ClipTokenizer:
             texts = [texts]
         out = np.zeros((len(texts), context_length), dtype=np.int32)
         for i, t in enumerate(texts):
-            ids = [self.bos_token_id] + self.encode(t, unescape_html=True) + [self.eos_token_id]
+            ids = [self.bos_token_id] + self.encode(t, openai=True) + [self.eos_token_id]
             if len(ids) > context_length:
                 if not truncate:
                     raise RuntimeError(f"Input {t} is too long for context length {context_length}")
