@@ -11,7 +11,10 @@ The reference tokenises on the host in two flavours:
 
 Both read the same published algorithm (OpenAI ``simple_tokenizer.py`` / ``transformers`` ``CLIPTokenizer``):
 NFC + whitespace collapse + lower-casing, a regex pre-split, bytes mapped to printable unicode, greedy
-lowest-rank-first pair merging with an ``</w>`` end-of-word marker.  The vocabulary / merge table are assets of the
+lowest-rank-first pair merging with an ``</w>`` end-of-word marker.  They differ in details that the two front ends
+keep apart: ``clip.tokenize`` un-escapes HTML entities, uses Python's ``\s`` (which includes U+001C..U+001F) and
+``str.lower()`` (word-final sigma); ``transformers`` uses Unicode ``White_Space`` and lower-cases character by
+character.  The vocabulary / merge table are assets of the
 checkpoint (``vocab.json`` + ``merges.txt``, or OpenAI's ``bpe_simple_vocab_16e6.txt.gz``) — none is on this box, so
 ``tests/test_tokenizer.py`` pins the implementation against ``transformers.CLIPTokenizer`` on a synthetic merge table.
 Host-side plumbing only: the device path starts at ``input_ids``.
@@ -63,8 +66,8 @@ def base_vocab() -> List[str]:
 
 
 def _clean(text: str, openai: bool) -> str:
-    if openai:   # basic_clean (minus ftfy, which is not installed) + whitespace_clean + lower
-        text = html.unescape(html.unescape(text)).strip()
+    if openai:   # basic_clean + whitespace_clean + lower; of ftfy.fix_text (not installed) only its NFC step is kept
+        text = html.unescape(html.unescape(unicodedata.normalize("NFC", text))).strip()
         return re.sub(r"\s+", " ", text).strip().lower()
     # transformers: normalizers.Sequence([NFC(), Replace(Regex(r"\s+"), " "), Lowercase()]).  `tokenizers` lowercases
     # character by character, i.e. without str.lower()'s context rule for a word-final capital sigma.
