@@ -72,6 +72,17 @@ def test_oracle_matches_pil_resize(h, w):
         assert np.array_equal(R.resize_crop_u8(a, nw, nh, left, top), _pil_tile(a, "floor"))
 
 
+def test_oracle_matches_pil_on_random_sizes():
+    """Seeded sweep over arbitrary (also non-aspect-preserving) size pairs, up- and down-scaling."""
+    rng = np.random.default_rng(2024)
+    for _ in range(25):
+        h, w = (int(v) for v in rng.integers(1, 400, 2))
+        nh, nw = (int(v) for v in rng.integers(1, 400, 2))
+        a = _img(rng, h, w, "noise" if rng.random() < 0.7 else "stripes")
+        ref = np.asarray(PIL.Image.fromarray(a).resize((nw, nh), resample=PIL.Image.BICUBIC))
+        assert np.array_equal(R.resize_bicubic_u8(a, nw, nh), ref), (h, w, nh, nw)
+
+
 def test_resize_plan_conventions():
     # floor = CLIPImageProcessor.center_crop, round = torchvision CenterCrop (banker's rounding of x.5)
     assert P.resize_plan(224, 224) == (224, 224, 0, 0)
