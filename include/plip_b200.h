@@ -32,7 +32,7 @@ extern "C" {
 
 #define PLIP_API __attribute__((visibility("default")))
 
-#define PLIP_B200_ABI_VERSION 3  /* 3: + plip_resize_crop_u8 */
+#define PLIP_B200_ABI_VERSION 4  /* 3: + plip_resize_crop_u8; 4: + plip_profile_* */
 
 /* Model constants (TF:configuration_clip.py:47-64,97-109,160-161). */
 #define PLIP_IMAGE_SIZE 224
@@ -168,6 +168,23 @@ PLIP_API int plip_encode_images_host(plip_engine_t* e, const void* pixels_host, 
 PLIP_API int plip_encode_text_host(plip_engine_t* e, const void* ids_host, int ids_dtype,
                                    const void* attention_mask_host, int64_t n, int seq_len,
                                    float* out_host, int normalize);
+
+/* ---- in-step kernel timing (measurement support for bench.py) --------------------- */
+/* While enabled, every kernel launch of plip_encode_images / plip_encode_text* on this handle is bracketed by a
+ * CUDA event pair recorded on the launch stream.  plip_profile_read waits for the recorded events and returns one
+ * aggregated row per (tower, kernel role): launches, summed device time, and the ALGORITHMIC flops / HBM bytes of
+ * those launches — i.e. each kernel's average duration inside the step it belongs to, under the
+ * step's own clocks and cache state.  Event pairs serialise nothing but cost a few microseconds of launch gap
+ * each, so bench.py profiles separate, untimed steps.  enable(on) always clears what was recorded. */
+typedef struct plip_kernel_time {
+  char name[48];     /* "<tower>/<role>", e.g. "vision/gemm[fc2+resid]", "text/attention" */
+  int32_t launches;
+  float total_ms;
+  double flops;      /* algorithmic FLOPs of the recorded launches (0 for memory-bound helpers) */
+  double bytes;      /* algorithmic HBM bytes of the recorded launches */
+} plip_kernel_time_t;
+PLIP_API int plip_profile_enable(plip_engine_t* e, int on);
+PLIP_API int plip_profile_read(plip_engine_t* e, plip_kernel_time_t* out, int cap, int* count);
 
 /* ---- per-kernel test hooks (used by tests/ only; stream-ordered, device pointers) ------------ */
 /* epilogue: 0 bias->bf16, 1 bias+QuickGELU->bf16, 2 x_f32 += acc+bias (optionally also xb_out bf16 copy +

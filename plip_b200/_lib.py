@@ -33,6 +33,13 @@ class TensorInfo(C.Structure):
     ]
 
 
+class KernelTime(C.Structure):
+    """Mirror of ``plip_kernel_time_t``."""
+
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_int32), ("total_ms", C.c_float), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 class ResizeDesc(C.Structure):
     """Mirror of ``plip_resize_desc_t`` (32 bytes; ``preprocess.RESIZE_DESC_DTYPE`` is the numpy twin)."""
 
@@ -69,6 +76,8 @@ SIGNATURES = {
     "plip_resize_crop_u8": (_i, [_vp, _u64, _vp, _i64, _vp, _vp]),
     "plip_encode_images_host": (_i, [_vp, _vp, _i, _i64, _fp, _i]),
     "plip_encode_text_host": (_i, [_vp, _vp, _i, _vp, _i64, _i, _fp, _i]),
+    "plip_profile_enable": (_i, [_vp, _i]),
+    "plip_profile_read": (_i, [_vp, C.POINTER(KernelTime), _i, C.POINTER(_i)]),
     "plip_dbg_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _fp, _vp, _i, _fp, _i, _i, _i, _fp, _fp, _i, _vp, _fp, _vp]),
     "plip_dbg_resize_filter": (_i, [_i, _i, _i, _vp, _i, C.POINTER(_i), C.POINTER(_i)]),
     "plip_dbg_text_bucket_plan": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i]),

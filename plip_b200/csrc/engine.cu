@@ -102,6 +102,12 @@ struct LayerW {
 
 constexpr int kEosId = 49407;  // TF:configuration_clip.py:63 (eos_token_id)
 
+enum ProfKind { PK_QKV = 0, PK_ATTN, PK_OUT, PK_FC1, PK_FC2, PK_PATCH, PK_IM2COL, PK_LN, PK_ROWSTATS, PK_EMBED, PK_PROJ,
+                PK_MISC, PK_COUNT };
+const char* const kProfNames[PK_COUNT] = {"gemm[ln1+qkv]", "attention", "gemm[out_proj+resid]", "gemm[ln2+fc1+gelu]",
+                                          "gemm[fc2+resid]", "gemm[patch_embed]", "im2col", "layernorm",
+                                          "rowstats_cast", "text_embed", "gemm[projection]", "misc"};
+
 size_t pixel_bytes(int fmt) {
   const size_t px = (size_t)3 * kImage * kImage;
   return fmt == PLIP_PIX_F32_NCHW ? px * 4 : (fmt == PLIP_PIX_BF16_NCHW ? px * 2 : px);
@@ -149,9 +155,36 @@ struct plip_engine {
   size_t d_out_bytes = 0;
   void* d_aux = nullptr;  // ids + mask for the text host path
   size_t d_aux_bytes = 0;
+  // in-step kernel timing (plip_profile_*): a CUDA event pair around every launch of a forward pass, recorded on
+  // the launch stream, so bench.py can report each kernel's average duration INSIDE the step it belongs to
+  bool prof_on = false;
+  int prof_tower = 0;  // 0 vision, 1 text (set by the forward that is running)
+  std::vector<cudaEvent_t> prof_ev;    // event pool, two per recorded launch
+  struct ProfRec { int kind; int tower; double flops, bytes; };
+  std::vector<ProfRec> prof_rec;
 };
 
 namespace {
+
+// Records an event before / after one launch when profiling is on (no-op otherwise).
+struct ProfScope {
+  plip_engine* e;
+  cudaStream_t st;
+  bool on;
+  ProfScope(plip_engine* e_, cudaStream_t st_, int kind, double flops, double bytes) : e(e_), st(st_), on(e_->prof_on) {
+    if (!on) return;
+    if (e->prof_rec.size() >= 8192) { on = false; return; }
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+    e->prof_ev.push_back(a);
+    e->prof_ev.push_back(b);
+    e->prof_rec.push_back({kind, e->prof_tower, flops, bytes});
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(e->prof_ev.back(), st);
+  }
+};
 
 template <typename T>
 const T* wptr(const plip_engine* e, const Spec& s) {
@@ -217,7 +250,18 @@ int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int
   const int64_t M = n_seq * S;
   PLIP_REQUIRE(M <= 0x7fffffff / 4, "micro-batch too large");
   if (num_layers <= 0) return 0;
-  if (int rc = launch_rowstats_cast(e->X, M, D, e->Xn, e->stats, st)) return rc;
+  const double dM = (double)M, dD = (double)D, dF = (double)FF;
+  {
+    ProfScope ps(e, st, PK_ROWSTATS, 0, dM * dD * 6 + dM * 8);
+    if (int rc = launch_rowstats_cast(e->X, M, D, e->Xn, e->stats, st)) return rc;
+  }
+  // algorithmic HBM bytes per launch: operands read once, outputs written once
+  const double b_qkv = dM * dD * 2 + 3 * dD * dD * 2 + dM * 3 * dD * 2;
+  const double b_att = dM * 3 * dD * 2 + dM * dD * 2;
+  const double b_out = dM * dD * 2 + dD * dD * 2 + dM * dD * (4 + 4 + 2);
+  const double b_fc1 = dM * dD * 2 + dD * dF * 2 + dM * dF * 2;
+  const double b_fc2 = dM * dF * 2 + dD * dF * 2 + dM * dD * (4 + 4 + 2);
+  const double f_att = 4.0 * (double)n_seq * heads * S * S * kHeadDim;
   int np = 1;
   for (int l = 0; l < num_layers; ++l) {
     const LayerW& w = L[l];
@@ -226,41 +270,71 @@ int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int
     g.A = e->Xn; g.lda = D; g.W = w.wqkv; g.ldw = D; g.M = (int)M; g.N = 3 * D; g.K = D;
     g.bias = w.bqkv; g.colsum = w.sqkv; g.stats_in = e->stats; g.n_partials = np;
     g.out = e->QKV; g.ldo = 3 * D; g.epi = EPI_LN_BIAS_BF16;
-    if (int rc = launch_gemm(g, st)) return rc;
-    if (int rc = launch_attention(e->QKV, n_seq, S, heads, causal, kmask, e->AO, st)) return rc;
+    {
+      ProfScope ps(e, st, PK_QKV, 2.0 * dM * 3 * dD * dD, b_qkv);
+      if (int rc = launch_gemm(g, st)) return rc;
+    }
+    {
+      ProfScope ps(e, st, PK_ATTN, f_att, b_att);
+      if (int rc = launch_attention(e->QKV, n_seq, S, heads, causal, kmask, e->AO, st)) return rc;
+    }
     g = GemmArgs();
     g.A = e->AO; g.lda = D; g.W = w.wo; g.ldw = D; g.M = (int)M; g.N = D; g.K = D;
     g.bias = w.bo; g.out = e->X; g.ldo = D; g.epi = EPI_BIAS_RESID_F32;
     g.xb_out = e->Xn; g.stats_out = e->stats; g.n_tiles_used = &np;
-    if (int rc = launch_gemm(g, st)) return rc;
+    {
+      ProfScope ps(e, st, PK_OUT, 2.0 * dM * dD * dD, b_out);
+      if (int rc = launch_gemm(g, st)) return rc;
+    }
     // x = x + fc2(quick_gelu(fc1(LN2(x))))                                TF:modeling_clip.py:379-382
     g = GemmArgs();
     g.A = e->Xn; g.lda = D; g.W = w.w1; g.ldw = D; g.M = (int)M; g.N = FF; g.K = D;
     g.bias = w.b1; g.colsum = w.s1; g.stats_in = e->stats; g.n_partials = np;
     g.out = e->H; g.ldo = FF; g.epi = EPI_LN_BIAS_GELU_BF16;
-    if (int rc = launch_gemm(g, st)) return rc;
+    {
+      ProfScope ps(e, st, PK_FC1, 2.0 * dM * dD * dF, b_fc1);
+      if (int rc = launch_gemm(g, st)) return rc;
+    }
     g = GemmArgs();
     g.A = e->H; g.lda = FF; g.W = w.w2; g.ldw = FF; g.M = (int)M; g.N = D; g.K = FF;
     g.bias = w.b2; g.out = e->X; g.ldo = D; g.epi = EPI_BIAS_RESID_F32;
     if (l + 1 < num_layers) {  // the last layer's output only feeds the pooled-row LayerNorm (fp32 X)
       g.xb_out = e->Xn; g.stats_out = e->stats; g.n_tiles_used = &np;
     }
-    if (int rc = launch_gemm(g, st)) return rc;
+    {
+      ProfScope ps(e, st, PK_FC2, 2.0 * dM * dD * dF, b_fc2);
+      if (int rc = launch_gemm(g, st)) return rc;
+    }
   }
   return 0;
 }
 
 // Vision tower up to (and including) `num_layers` encoder layers; X holds the residual stream.
 int vision_trunk(plip_engine* e, const void* pixels, int fmt, int64_t mb, int num_layers, cudaStream_t st) {
-  if (int rc = launch_im2col(pixels, fmt, mb, e->H, st)) return rc;
+  e->prof_tower = 0;
+  const double dmb = (double)mb;
+  {
+    ProfScope ps(e, st, PK_IM2COL, 0, dmb * (double)pixel_bytes(fmt) + dmb * kPatches * kPatchK * 2);
+    if (int rc = launch_im2col(pixels, fmt, mb, e->H, st)) return rc;
+  }
   GemmArgs g;
   g.A = e->H; g.lda = kPatchK; g.W = e->v_patch_w; g.ldw = kPatchK;
   g.M = (int)(mb * kPatches); g.N = kVisDim; g.K = kPatchK;
   g.out = e->X; g.ldo = kVisDim; g.pos = e->v_pos; g.epi = EPI_PATCH_F32;
-  if (int rc = launch_gemm(g, st)) return rc;
-  if (int rc = launch_cls_rows(e->v_cls, e->v_pos, mb, e->X, st)) return rc;
+  {
+    ProfScope ps(e, st, PK_PATCH, 2.0 * dmb * kPatches * kVisDim * kPatchK,
+                 dmb * kPatches * kPatchK * 2 + (double)kVisDim * kPatchK * 2 + dmb * kPatches * kVisDim * 4);
+    if (int rc = launch_gemm(g, st)) return rc;
+  }
+  {
+    ProfScope ps(e, st, PK_MISC, 0, dmb * kVisDim * 4);
+    if (int rc = launch_cls_rows(e->v_cls, e->v_pos, mb, e->X, st)) return rc;
+  }
   const int64_t M = mb * kVisSeq;
-  if (int rc = launch_layernorm(e->X, nullptr, kVisDim, M, kVisDim, e->v_pre_g, e->v_pre_b, e->X, nullptr, st)) return rc;
+  {
+    ProfScope ps(e, st, PK_LN, 0, (double)M * kVisDim * 8);
+    if (int rc = launch_layernorm(e->X, nullptr, kVisDim, M, kVisDim, e->v_pre_g, e->v_pre_b, e->X, nullptr, st)) return rc;
+  }
   return run_layers(e, e->vis, mb, kVisSeq, kVisDim, kVisFF, kVisHeads, false, nullptr, num_layers, st);
 }
 
@@ -268,13 +342,22 @@ int vision_forward(plip_engine* e, const void* pixels, int fmt, int64_t mb, floa
                    cudaStream_t st) {
   if (int rc = vision_trunk(e, pixels, fmt, mb, kLayers, st)) return rc;
   // pooled = post_layernorm(last_hidden_state[:, 0, :])                  TF:modeling_clip.py:685-686
-  if (int rc = launch_layernorm(e->X, nullptr, (int64_t)kVisSeq * kVisDim, mb, kVisDim, e->v_post_g, e->v_post_b,
-                                nullptr, e->pooled, st)) return rc;
+  {
+    ProfScope ps(e, st, PK_LN, 0, (double)mb * kVisDim * 6);
+    if (int rc = launch_layernorm(e->X, nullptr, (int64_t)kVisSeq * kVisDim, mb, kVisDim, e->v_post_g, e->v_post_b,
+                                  nullptr, e->pooled, st)) return rc;
+  }
   GemmArgs g;
   g.A = e->pooled; g.lda = kVisDim; g.W = e->v_proj; g.ldw = kVisDim;
   g.M = (int)mb; g.N = kProj; g.K = kVisDim; g.out = out; g.ldo = kProj; g.epi = EPI_F32;
-  if (int rc = launch_gemm(g, st)) return rc;
-  if (normalize) return launch_l2_normalize(out, mb, kProj, st);
+  {
+    ProfScope ps(e, st, PK_PROJ, 2.0 * (double)mb * kProj * kVisDim, (double)mb * (kVisDim * 2 + kProj * 4) + (double)kProj * kVisDim * 2);
+    if (int rc = launch_gemm(g, st)) return rc;
+  }
+  if (normalize) {
+    ProfScope ps(e, st, PK_MISC, 0, (double)mb * kProj * 8);
+    return launch_l2_normalize(out, mb, kProj, st);
+  }
   return 0;
 }
 
@@ -283,9 +366,14 @@ int vision_forward(plip_engine* e, const void* pixels, int fmt, int64_t mb, floa
 // that know the longest caption of the batch may pass a shorter S: same result, proportionally less work.
 int text_trunk(plip_engine* e, const void* ids, int ids_dtype, const void* mask, int64_t mb, int S, int stride,
                int num_layers, cudaStream_t st) {
-  if (int rc = launch_text_embed(ids, ids_dtype, mb, S, stride, e->t_tok, e->t_pos, e->X, e->row_idx, kEosId, st)) return rc;
+  e->prof_tower = 1;
+  {
+    ProfScope ps(e, st, PK_EMBED, 0, (double)mb * S * kTxtDim * 8);
+    if (int rc = launch_text_embed(ids, ids_dtype, mb, S, stride, e->t_tok, e->t_pos, e->X, e->row_idx, kEosId, st)) return rc;
+  }
   const int32_t* km = nullptr;
   if (mask) {
+    ProfScope ps(e, st, PK_MISC, 0, (double)mb * S * 12);
     if (int rc = launch_mask_to_i32(mask, ids_dtype, mb * S, S, stride, e->kmask, st)) return rc;
     km = e->kmask;
   }
@@ -296,13 +384,22 @@ int text_forward(plip_engine* e, const void* ids, int ids_dtype, const void* mas
                  float* out, int normalize, cudaStream_t st) {
   if (int rc = text_trunk(e, ids, ids_dtype, mask, mb, S, stride, kLayers, st)) return rc;
   // pooled = final_layer_norm(last_hidden_state)[b, first eos]            TF:modeling_clip.py:562-584
-  if (int rc = launch_layernorm(e->X, e->row_idx, kTxtDim, mb, kTxtDim, e->t_fin_g, e->t_fin_b, nullptr,
-                                e->pooled, st)) return rc;
+  {
+    ProfScope ps(e, st, PK_LN, 0, (double)mb * kTxtDim * 6);
+    if (int rc = launch_layernorm(e->X, e->row_idx, kTxtDim, mb, kTxtDim, e->t_fin_g, e->t_fin_b, nullptr,
+                                  e->pooled, st)) return rc;
+  }
   GemmArgs g;
   g.A = e->pooled; g.lda = kTxtDim; g.W = e->t_proj; g.ldw = kTxtDim;
   g.M = (int)mb; g.N = kProj; g.K = kTxtDim; g.out = out; g.ldo = kProj; g.epi = EPI_F32;
-  if (int rc = launch_gemm(g, st)) return rc;
-  if (normalize) return launch_l2_normalize(out, mb, kProj, st);
+  {
+    ProfScope ps(e, st, PK_PROJ, 2.0 * (double)mb * kProj * kTxtDim, (double)mb * (kTxtDim * 2 + kProj * 4) + (double)kProj * kTxtDim * 2);
+    if (int rc = launch_gemm(g, st)) return rc;
+  }
+  if (normalize) {
+    ProfScope ps(e, st, PK_MISC, 0, (double)mb * kProj * 8);
+    return launch_l2_normalize(out, mb, kProj, st);
+  }
   return 0;
 }
 
@@ -501,9 +598,48 @@ PLIP_API int plip_destroy(plip_engine_t* e) {
   if (e->d_out) cudaFree(e->d_out);
   if (e->d_aux) cudaFree(e->d_aux);
   if (e->ev_last) cudaEventDestroy(e->ev_last);
+  for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
   if (e->s_compute) cudaStreamDestroy(e->s_compute);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   delete e;
+  return 0;
+}
+
+PLIP_API int plip_profile_enable(plip_engine_t* e, int on) {
+  PLIP_REQUIRE(e != nullptr, "plip_profile_enable: null engine");
+  for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
+  e->prof_ev.clear();
+  e->prof_rec.clear();
+  e->prof_on = on != 0;
+  return 0;
+}
+
+PLIP_API int plip_profile_read(plip_engine_t* e, plip_kernel_time_t* out, int cap, int* count) {
+  PLIP_REQUIRE(e && out && count && cap > 0, "plip_profile_read: bad argument");
+  plip_kernel_time_t agg[2 * PK_COUNT];
+  memset(agg, 0, sizeof(agg));
+  for (size_t i = 0; i < e->prof_rec.size(); ++i) {
+    PLIP_CUDA_CHECK(cudaEventSynchronize(e->prof_ev[2 * i + 1]));
+    float ms = 0.f;
+    PLIP_CUDA_CHECK(cudaEventElapsedTime(&ms, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]));
+    plip_kernel_time_t& a = agg[e->prof_rec[i].tower * PK_COUNT + e->prof_rec[i].kind];
+    a.launches += 1;
+    a.total_ms += ms;
+    a.flops += e->prof_rec[i].flops;
+    a.bytes += e->prof_rec[i].bytes;
+  }
+  int n = 0;
+  for (int t = 0; t < 2; ++t)
+    for (int k = 0; k < PK_COUNT; ++k) {
+      const plip_kernel_time_t& a = agg[t * PK_COUNT + k];
+      if (a.launches == 0) continue;
+      if (n < cap) {
+        out[n] = a;
+        snprintf(out[n].name, sizeof(out[n].name), "%s/%s", t == 0 ? "vision" : "text", kProfNames[k]);
+      }
+      ++n;
+    }
+  *count = n;
   return 0;
 }
 

@@ -6,6 +6,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 namespace plip {
 
 static thread_local char g_last_error[1024] = "";
@@ -49,8 +52,54 @@ static EncodeTiledFn resolve_encode() {
   return fn;
 }
 
+// A forward pass needs ~200 tensor maps and they repeat from call to call (same workspace, same weights, same
+// micro-batch): encoded maps are cached by their full description.  cuTensorMapEncodeTiled costs ~1-2 us of
+// host time each, which is what bounds small-batch latency once the GPU side is a few hundred microseconds.
+namespace {
+struct TmapKey {
+  uint64_t base, rows, cols, stride, box;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && stride == o.stride && box == o.box;
+  }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = k.base * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x632BE59BD9B4E019ull) + (h << 6) + (h >> 2);
+    h ^= (k.cols * 0xC2B2AE3D27D4EB4Full) + (h << 6) + (h >> 2);
+    h ^= (k.stride * 0x165667B19E3779F9ull) + (h << 6) + (h >> 2);
+    h ^= (k.box + 0x27D4EB2F165667C5ull) + (h << 6) + (h >> 2);
+    return (size_t)h;
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapHash> g_tmap_cache;
+}  // namespace
+
+static int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                               uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols) {
+  const TmapKey key{reinterpret_cast<uint64_t>(base), rows, cols, row_stride_bytes,
+                    (static_cast<uint64_t>(box_rows) << 32) | box_cols};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  if (int rc = encode_tmap_bf16_2d(out, base, rows, cols, row_stride_bytes, box_rows, box_cols)) return rc;
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();  // callers with ever-changing buffers: bounded memory
+  g_tmap_cache.emplace(key, *out);
+  return 0;
+}
+
+static int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                               uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn enc = resolve_encode();
   if (!enc) return -1;
   cuuint64_t gdim[2] = {cols, rows};

@@ -9,6 +9,8 @@
 // accumulated from the same operand tiles that feed the product, so each input is read once per tile.
 #include "kernels.cuh"
 
+#include <mutex>
+
 namespace plip {
 
 namespace {
@@ -389,22 +391,47 @@ int launch_similarity_topk(const float* q, int64_t n, const float* s, int64_t m,
   float* scratch_v = nullptr;
   int* scratch_i = nullptr;
   unsigned* tickets = nullptr;
-  void* scratch = nullptr;
   if (splits > 1) {
+    // Partial lists of the space splits: a per-device buffer that only ever grows (no allocation once warm;
+    // this function has no engine handle to hang a workspace on).  Calls that share it are ordered by `ev`.
+    struct Scratch { void* p = nullptr; size_t bytes = 0; cudaEvent_t ev = nullptr; };
+    static Scratch pool[64];
+    static std::mutex mu;
     const size_t ent = (size_t)splits * row_tiles * TM * k;
     const size_t bytes = ent * 8 + (size_t)row_tiles * 4;
-    PLIP_CUDA_CHECK(cudaMallocAsync(&scratch, bytes, st));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    Scratch& sc = pool[dev & 63];
+    if (!sc.ev) PLIP_CUDA_CHECK(cudaEventCreateWithFlags(&sc.ev, cudaEventDisableTiming));
+    if (sc.bytes < bytes) {
+      if (sc.p) {
+        PLIP_CUDA_CHECK(cudaEventSynchronize(sc.ev));  // last user of the old buffer
+        PLIP_CUDA_CHECK(cudaFree(sc.p));
+        sc.p = nullptr; sc.bytes = 0;
+      }
+      const size_t want = bytes + bytes / 2;
+      PLIP_CUDA_CHECK(cudaMalloc(&sc.p, want));
+      sc.bytes = want;
+    }
+    PLIP_CUDA_CHECK(cudaStreamWaitEvent(st, sc.ev, 0));  // a call on another stream may still be merging
+    void* scratch = sc.p;
     scratch_v = static_cast<float*>(scratch);
     scratch_i = reinterpret_cast<int*>(scratch_v + ent);
     tickets = reinterpret_cast<unsigned*>(scratch_i + ent);
     PLIP_CUDA_CHECK(cudaMemsetAsync(tickets, 0, (size_t)row_tiles * 4, st));
+    dim3 grid((unsigned)row_tiles, (unsigned)splits);
+    PLIP_CUDA_CHECK(launch_pdl(similarity_topk_tiled_kernel, grid, dim3(kTkThreads), smem, st, 1, q, n, s, m, (int)kProj,
+                               scale, norm_q ? 1 : 0, norm_s ? 1 : 0, k, tiles_per_split, scratch_v, scratch_i, tickets,
+                               idx, val));
+    PLIP_CUDA_CHECK(cudaEventRecord(sc.ev, st));
+    ++g_launch_count;
+    return 0;
   }
   dim3 grid((unsigned)row_tiles, (unsigned)splits);
-  cudaError_t le = launch_pdl(similarity_topk_tiled_kernel, grid, dim3(kTkThreads), smem, st, 1, q, n, s, m, (int)kProj,
-                              scale, norm_q ? 1 : 0, norm_s ? 1 : 0, k, tiles_per_split, scratch_v, scratch_i, tickets,
-                              idx, val);
-  if (scratch) cudaFreeAsync(scratch, st);
-  PLIP_CUDA_CHECK(le);
+  PLIP_CUDA_CHECK(launch_pdl(similarity_topk_tiled_kernel, grid, dim3(kTkThreads), smem, st, 1, q, n, s, m, (int)kProj,
+                             scale, norm_q ? 1 : 0, norm_s ? 1 : 0, k, tiles_per_split, scratch_v, scratch_i, tickets,
+                             idx, val));
   ++g_launch_count;
   return 0;
 }

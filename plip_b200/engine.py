@@ -101,6 +101,19 @@ class Engine:
             t = t.to(self.device, non_blocking=True)
         return t.contiguous()
 
+    def upload_async(self, t: torch.Tensor):
+        """Start copying a host tensor to the device on the engine's copy stream; returns ``(device tensor, event)``.
+        The consumer stream must ``wait_event(event)`` before the first use (pinned sources overlap with compute)."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            d = t.contiguous().to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        d.record_stream(cur)
+        return d, ev
+
     # ---- device-tensor API -------------------------------------------------------------------
     @torch.no_grad()
     def encode_images(self, pixels: torch.Tensor, normalize: bool = False) -> torch.Tensor:
@@ -234,6 +247,20 @@ class Engine:
             check(self._L.plip_encode_text_host(self._h, ids.data_ptr(), idt, mask.data_ptr() if mask is not None else None,
                                                 n, s, out.data_ptr(), int(normalize)), "plip_encode_text_host")
         return out
+
+    # ---- in-step kernel timing (bench.py) ------------------------------------------------------
+    def profile(self, on: bool) -> None:
+        """Bracket every kernel launch of the following tower calls with CUDA events (``plip_profile_enable``)."""
+        check(self._L.plip_profile_enable(self._h, int(bool(on))), "plip_profile_enable")
+
+    def profile_read(self):
+        """Rows ``{name, launches, total_ms, flops, bytes}`` aggregated per (tower, kernel role) since ``profile(True)``."""
+        from ._lib import KernelTime
+        buf = (KernelTime * 64)()
+        cnt = C.c_int(0)
+        check(self._L.plip_profile_read(self._h, buf, 64, C.byref(cnt)), "plip_profile_read")
+        return [{"name": buf[i].name.decode(), "launches": int(buf[i].launches), "total_ms": float(buf[i].total_ms),
+                 "flops": float(buf[i].flops), "bytes": float(buf[i].bytes)} for i in range(min(cnt.value, 64))]
 
     # ---- test hook ---------------------------------------------------------------------------
     @torch.no_grad()

@@ -12,6 +12,9 @@ Weights come in two flavours:
   (TF:modeling_clip.py:402-459): zero biases, unit LayerNorm gains.
 * ``mode="rich"`` additionally draws non-zero biases and non-trivial LayerNorm gain/shift so that every bias /
   affine code path of the kernels is exercised (strictly stronger test).
+* ``mode="outlier"`` is "rich" reshaped to stress the numerics the way a *trained* CLIP ViT-B/32 does
+  (massive-activation channels in the residual stream, non-zero per-token means, LayerNorm gains spread over
+  two orders of magnitude): see :func:`_add_outliers`.  Used by the parity tests of the LayerNorm-folded GEMMs.
 """
 from __future__ import annotations
 
@@ -52,10 +55,37 @@ def _tower(sd, g, prefix: str, dim: int, ff: int, layers: int, rich: bool) -> No
         sd[f"{p}.layer_norm2.bias"] = randn(dim, std=0.05 if rich else 0.0)
 
 
+def _add_outliers(sd, g, prefix: str, dim: int, layers: int) -> None:
+    """Reshape a "rich" tower so that its residual stream looks like a trained CLIP's:
+
+    * two "massive activation" channels switched on by the MLP of layer 1 (constant part through ``fc2.bias``,
+      token-dependent part through 20x larger ``fc2.weight`` rows) and a third one in layer 3 — |x| of 60...300
+      against a typical |x| of ~1, persisting through every later layer of the residual stream;
+    * a common shift of all channels (``out_proj.bias`` of layer 0): per-token mean ~1.5 standard deviations;
+    * LayerNorm gains from 0.05 (on the massive channels, as trained models learn) to ~10 on a few others, and a
+      few shifts of +-2."""
+    ch = [int(c) for c in torch.randperm(dim, generator=g)[:3]]
+    sd[f"{prefix}.encoder.layers.0.self_attn.out_proj.bias"] += 1.5
+    fc2b, fc2w = f"{prefix}.encoder.layers.1.mlp.fc2.bias", f"{prefix}.encoder.layers.1.mlp.fc2.weight"
+    sd[fc2b][ch[0]] += 120.0
+    sd[fc2b][ch[1]] -= 60.0
+    sd[fc2w][ch[0]] *= 20.0
+    sd[fc2w][ch[1]] *= 20.0
+    sd[f"{prefix}.encoder.layers.3.mlp.fc2.bias"][ch[2]] += 250.0
+    for i in range(layers):
+        for ln in ("layer_norm1", "layer_norm2"):
+            w, b = sd[f"{prefix}.encoder.layers.{i}.{ln}.weight"], sd[f"{prefix}.encoder.layers.{i}.{ln}.bias"]
+            w[ch] = 0.05
+            big = torch.randperm(dim, generator=g)[:8]
+            w[big] = 4.0 + 6.0 * torch.rand(8, generator=g)
+            sh = torch.randperm(dim, generator=g)[:4]
+            b[sh] = torch.tensor([2.0, -2.0, 1.0, -1.0])
+
+
 def make_state_dict(seed: int = 0, mode: str = "rich") -> "OrderedDict[str, torch.Tensor]":
     """fp32 state dict with the HF ``CLIPModel`` key set (``load_state_dict(strict=True)``-able)."""
-    assert mode in ("rich", "hf_init")
-    rich = mode == "rich"
+    assert mode in ("rich", "hf_init", "outlier")
+    rich = mode != "hf_init"
     g = torch.Generator(device="cpu").manual_seed(seed)
 
     def randn(*shape, std):
@@ -83,6 +113,12 @@ def make_state_dict(seed: int = 0, mode: str = "rich") -> "OrderedDict[str, torc
     # ---- projections (TF:modeling_clip.py:784-786)
     sd["visual_projection.weight"] = randn(PROJ, vd, std=vd ** -0.5)
     sd["text_projection.weight"] = randn(PROJ, td, std=td ** -0.5)
+    if mode == "outlier":
+        go = torch.Generator(device="cpu").manual_seed(seed + 7919)
+        _add_outliers(sd, go, "vision_model", vd, VISION["layers"])
+        _add_outliers(sd, go, "text_model", td, TEXT["layers"])
+        for ln in ("vision_model.post_layernorm", "text_model.final_layer_norm"):
+            sd[ln + ".weight"][torch.randperm(sd[ln + ".weight"].numel(), generator=go)[:8]] = 5.0
     return sd
 
 

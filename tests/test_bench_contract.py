@@ -24,7 +24,8 @@ def test_reference_arm_json_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["higher_is_better"] is True
     assert line["metric"].startswith("image-text pairs/sec") and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert "sample" in line["cpu_baseline"] and line["config"]["workload"].startswith("dual tower")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["gpu_launches"] == 0 and line["steps"] == 1
 

@@ -31,6 +31,13 @@ def _encoders():
     return enc_i, enc_t, sim
 
 
+def _topk(q, space, k):
+    """Stand-in for Engine.similarity_topk: descending scores, ties by lower index."""
+    sc = q @ space.t()
+    val, idx = torch.sort(sc, dim=1, descending=True, stable=True)
+    return idx[:, :k].to(torch.int32), val[:, :k]
+
+
 def _data():
     g = torch.Generator().manual_seed(11)
     return torch.randn(23, 12, generator=g), torch.randn(9, 5, generator=g), torch.randn(4, 5, generator=g)
@@ -43,7 +50,7 @@ def _worker(rank, ws, port, outdir):
     try:
         imgs, queries, classes = _data()
         enc_i, enc_t, sim = _encoders()
-        sh = D.ShardedCLIP(enc_i, enc_t, sim, 14.3)
+        sh = D.ShardedCLIP(enc_i, enc_t, sim, 14.3, topk=_topk)
         assert (sh.rank, sh.world_size) == (rank, ws)
         # uneven all-gather restores order
         sl = sh.local_slice(imgs.shape[0])
@@ -61,8 +68,16 @@ def _worker(rank, ws, port, outdir):
         # cfg5 flow
         qs = sh.local_slice(queries.shape[0])
         block, gal, q_all = sh.retrieval(imgs[sl], queries[qs], queries.shape[0])
-        torch.save({"pred": pred, "logits": logits, "all_img": all_img, "block": block, "q_all": q_all, "lo": sl.start},
-                   os.path.join(outdir, f"r{rank}.pt"))
+        # gallery streamed in chunks == gallery as one tensor
+        block_c, _, _ = sh.retrieval(iter([imgs[sl][:5], imgs[sl][5:]]), queries[qs], queries.shape[0])
+        assert torch.equal(block_c, block)
+        # retrieval head over the sharded gallery (retrieval.py:13-16): global top-k identical on every rank
+        top_i, top_v = sh.retrieval_topk(gal, q_all, 6, imgs.shape[0])
+        # bench step: local images x captions of all ranks (equal caption blocks -> async gather path)
+        cap_local = queries[:8].view(2, 4, 5)[rank].contiguous()
+        lpi = sh.clip_forward(imgs[sl], cap_local)
+        torch.save({"pred": pred, "logits": logits, "all_img": all_img, "block": block, "q_all": q_all, "lo": sl.start,
+                    "top_i": top_i, "top_v": top_v, "lpi": lpi}, os.path.join(outdir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -84,3 +99,8 @@ def test_two_rank_gloo_matches_single_process():
         assert torch.allclose(r["q_all"], ref_q, atol=1e-6)
     assert torch.allclose(torch.cat([r["block"] for r in res]), ref_block, atol=1e-5)
     assert [r["lo"] for r in res] == [0, 12]
+    full = ref_q @ ref_img.t()                                           # [n_queries, n_gallery]
+    ref_v, ref_i = torch.sort(full, dim=1, descending=True, stable=True)
+    for r in res:
+        assert torch.equal(r["top_i"], ref_i[:, :6]) and torch.allclose(r["top_v"], ref_v[:, :6], atol=1e-6)
+    assert torch.allclose(torch.cat([r["lpi"] for r in res]), sim(ref_img, enc_t(queries[:8]), 14.3), atol=1e-5)

@@ -119,7 +119,8 @@ def test_similarity_head_and_clip_forward(state_dict, golden):
     ids, mask = synth.token_ids(8)
     out = model(input_ids=ids.cuda(), pixel_values=px.cuda(), attention_mask=mask.cuda())
     assert out.logits_per_image.shape == (8, 8)
-    assert (out.logits_per_image.cpu() - _t(golden["logits_per_image"])).abs().max().item() < 3e-2
+    # measured bound of the bf16-operand contract on this 8 x 8 block (emulated max 8e-3, GPU r1 3.3e-3 on 4 x 4)
+    assert (out.logits_per_image.cpu() - _t(golden["logits_per_image"])).abs().max().item() < 1.0e-2
     assert torch.equal(out.logits_per_text, out.logits_per_image.t())
     assert (1 - O.cosine(out.image_embeds.cpu(), _t(golden["image_embeds"]))).max().item() < COS_TOL
     assert (1 - O.cosine(out.text_embeds.cpu(), _t(golden["text_embeds"]))).max().item() < COS_TOL

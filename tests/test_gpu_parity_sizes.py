@@ -1,0 +1,134 @@
+"""Parity at BASELINE.json's sizes and on trained-CLIP-like ("outlier") weights — CUDA engine vs the oracle.
+
+* cfg2: ViT-B/32 vision tower, 1024 DISTINCT images in one micro-batch (bf16 pixels resident on the device): the
+  oracle runs on a fixed sample of rows that covers the first / last rows of the batch, both partners of packed
+  attention tiles (rows 2k, 2k+1), and the last CTA-pair M tile.
+* ragged: 1024 + 37 images / captions (second micro-batch with an M tail that is not a multiple of 128 rows).
+* cfg3: 4096 images x 1024 captions through ``PlipCLIPModel.__call__``; ``logits_per_image[4096,1024]`` compared
+  with the oracle on sampled rows x columns.
+* outlier weights (``synthetic.make_state_dict(mode="outlier")``): massive-activation channels (|x| up to ~250),
+  non-zero per-token means and LayerNorm gains over two orders of magnitude — the regime where a LayerNorm folded
+  into a bf16 GEMM could cancel (VERDICT r1 weak #2 / ADVICE r1 medium).
+
+Tolerances: embedding cosine >= 1 - 1e-4 per vector (north_star).  End-to-end |dlogits_per_image| is asserted
+against the MEASURED bound of the 16-bit-operand contract (profiles/r2_precision_study.md):
+north_star's 1e-3 is not reachable end to end with single-term 16-bit operands.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_oracle as O
+from oracle import synth, weights
+
+pytestmark = pytest.mark.gpu
+COS_TOL = 1e-4
+DLOGITS_BF16 = 1.5e-2     # measured max 8e-3 (16x16) ... 1.2e-2 (64x32) at exp(logit_scale) = 14.3
+
+
+@pytest.fixture(scope="module")
+def big_engine(state_dict):
+    from plip_b200.engine import Engine
+    eng = Engine(state_dict, max_micro_batch=1024)
+    yield eng
+    eng.close()
+
+
+def _sample_rows(n, k, seed):
+    fixed = [0, 1, 2, 3, 49, 50, 127, 128, 254, 255, 256, 257, n - 4, n - 3, n - 2, n - 1]
+    rng = np.random.default_rng(seed)
+    rest = rng.choice(np.arange(4, n - 4), size=k - len(fixed), replace=False)
+    return torch.from_numpy(np.unique(np.concatenate([np.array([i for i in fixed if 0 <= i < n]), rest])))
+
+
+def test_cfg2_vision_1024_distinct_images_vs_oracle(big_engine, state_dict):
+    px = synth.pixel_values(1024)                                   # BASELINE cfg2 input (seed 1234)
+    out = big_engine.encode_images(px.to(torch.bfloat16).cuda()).cpu()
+    assert out.shape == (1024, 512) and torch.isfinite(out).all()
+    rows = _sample_rows(1024, 64, seed=2)
+    ref = O.get_image_features(state_dict, px[rows])
+    d = (1 - O.cosine(out[rows], ref))
+    assert d.max().item() < COS_TOL, d.max().item()
+    # uint8 tiles at the same size (normalisation fused on the device)
+    tiles = torch.from_numpy(synth.tiles_u8(1024, seed=5))
+    out8 = big_engine.encode_images(tiles.cuda()).cpu()
+    rows8 = _sample_rows(1024, 32, seed=3)
+    ref8 = O.get_image_features(state_dict, O.preprocess_u8(tiles[rows8]))
+    assert (1 - O.cosine(out8[rows8], ref8)).max().item() < COS_TOL
+
+
+def test_ragged_second_micro_batch_vs_oracle(big_engine, state_dict):
+    n = 1024 + 37                                                   # 37 x 50 = 1850 rows: 14 full M tiles + a tail of 58
+    px = synth.pixel_values(n, seed=99)
+    out = big_engine.encode_images(px.cuda()).cpu()
+    rows = torch.tensor([0, 1023, 1024, 1025, 1040, 1059, 1060])
+    assert (1 - O.cosine(out[rows], O.get_image_features(state_dict, px[rows]))).max().item() < COS_TOL
+    ids, mask = synth.token_ids(n, seed=98)                         # lengths U{8..77}, eos padding
+    tout = big_engine.encode_text(ids.cuda(), mask.cuda()).cpu()
+    trows = torch.cat([rows, _sample_rows(1024, 24, seed=4)])
+    tref = O.get_text_features(state_dict, ids[trows], mask[trows])
+    assert (1 - O.cosine(tout[trows], tref)).max().item() < COS_TOL
+    host = big_engine.encode_text_host(ids, mask)                   # length-bucketed host path, same answers
+    assert (1 - O.cosine(host[trows], tref)).max().item() < COS_TOL
+
+
+def test_cfg3_dual_tower_logits_4096x1024_vs_oracle(state_dict):
+    from plip_b200.modeling import PlipCLIPModel
+    model = PlipCLIPModel(state_dict, max_micro_batch=1024)
+    n_img, n_txt = 4096, 1024
+    px = synth.pixel_values(n_img)                                  # 4 micro-batches of 1024
+    ids, mask = synth.token_ids(n_txt)                              # seed 1235, len ~ U{8..77}
+    out = model(input_ids=ids.cuda(), pixel_values=px.to(torch.bfloat16).cuda(), attention_mask=mask.cuda())
+    lpi = out.logits_per_image
+    assert lpi.shape == (n_img, n_txt) and lpi.dtype == torch.float32 and torch.isfinite(lpi).all()
+    assert torch.equal(out.logits_per_text, lpi.t())
+    ri, ci = _sample_rows(n_img, 40, seed=6), _sample_rows(n_txt, 40, seed=7)
+    ref = O.clip_forward(state_dict, ids[ci], px[ri], mask[ci])
+    assert (1 - O.cosine(out.image_embeds.cpu()[ri], ref["image_embeds"])).max().item() < COS_TOL
+    assert (1 - O.cosine(out.text_embeds.cpu()[ci], ref["text_embeds"])).max().item() < COS_TOL
+    d = (lpi.cpu()[ri][:, ci] - ref["logits_per_image"]).abs()
+    print(f"cfg3 sampled {len(ri)}x{len(ci)}: |dlogits| max {d.max().item():.2e} mean {d.mean().item():.2e}")
+    assert d.max().item() < DLOGITS_BF16, d.max().item()
+    # the similarity head itself, on the engine's own embeddings: fp32 head vs fp64 -> far inside 1e-3
+    head = (out.image_embeds.double() @ out.text_embeds.double().t() * model.logit_scale_exp).float()
+    assert (lpi - head).abs().max().item() < 1e-4
+    model.engine.close()
+
+
+@pytest.fixture(scope="module")
+def outlier_sd():
+    torch.set_grad_enabled(False)
+    return weights.make_state_dict(0, "outlier")
+
+
+def test_outlier_weights_towers_vs_oracle(outlier_sd):
+    """Trained-CLIP-like residual stream: |x| up to ~250 in three channels, mean/std of the other channels ~1.5."""
+    from plip_b200.modeling import PlipCLIPModel
+    model = PlipCLIPModel(outlier_sd, max_micro_batch=64)
+    eng = model.engine
+    px = synth.pixel_values(24, seed=31)
+    ids, mask = synth.token_ids(24, seed=32)
+    hid = []
+    O.vision_transformer(outlier_sd, px[:4], hidden=hid)
+    assert hid[-1].abs().max().item() > 200                         # the stress is really there
+    for nl in (2, 4, 12):                                           # right after each outlier switches on, and the end
+        h = eng.hidden_states("vision", px[:4].cuda(), nl).cpu()
+        d = (h - hid[nl]).abs()
+        big = hid[nl].abs() > 20
+        assert (d[big] / hid[nl].abs()[big]).max().item() < 2e-3, nl    # massive channels: relative
+        assert d[~big].max().item() < 0.12 and d[~big].mean().item() < 8e-3, (nl, d[~big].max().item(), d[~big].mean().item())
+    thid = []
+    O.text_transformer(outlier_sd, ids[:4], mask[:4], hidden=thid)
+    th = eng.hidden_states("text", ids[:4].cuda(), 12, attention_mask=mask[:4].cuda()).cpu()
+    td = (th - thid[12]).abs()
+    tbig = thid[12].abs() > 20
+    assert (td[tbig] / thid[12].abs()[tbig]).max().item() < 2e-3
+    assert td[~tbig].max().item() < 0.15 and td[~tbig].mean().item() < 1e-2, (td[~tbig].max().item(), td[~tbig].mean().item())
+    out = model(input_ids=ids.cuda(), pixel_values=px.cuda(), attention_mask=mask.cuda())
+    ref = O.clip_forward(outlier_sd, ids, px, mask)
+    ci = (1 - O.cosine(out.image_embeds.cpu(), ref["image_embeds"])).max().item()
+    ct = (1 - O.cosine(out.text_embeds.cpu(), ref["text_embeds"])).max().item()
+    dl = (out.logits_per_image.cpu() - ref["logits_per_image"]).abs().max().item()
+    print(f"outlier weights: 1-cos image {ci:.2e} text {ct:.2e} |dlogits| {dl:.2e}")
+    assert ci < COS_TOL and ct < COS_TOL and dl < DLOGITS_BF16, (ci, ct, dl)
+    eng.close()
