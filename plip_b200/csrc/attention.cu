@@ -21,6 +21,8 @@
 // four CTAs co-reside per SM and hide each other's serial load -> MMA -> softmax -> MMA -> store chain.
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 namespace plip {
 
 namespace {
@@ -63,7 +65,7 @@ struct AttParams {
 };
 
 __global__ void __launch_bounds__(kAttThreads, kAttCtasPerSm)
-attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
+attention_kernel_v1(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
@@ -94,8 +96,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
       *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
 
   const int64_t num_tiles = p.seq_tiles * p.heads;
-  pdl_wait();
-  pdl_launch_dependents();
 
   if (warp == 4) {
     // ===================== TMA producer + MMA issuer =====================
@@ -280,6 +280,303 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
   if (warp == 0) tmem_dealloc<1>(tmem_base, kTmemCols);
 }
 
+// =====================================================================================================
+// v2 (round 2).  ncu on v1: ALU pipe 46 % busy, DRAM 38 %, tensor 14 % — the kernel was bound by the INSTRUCTION
+// COUNT of the softmax (per-element bit tests in two passes over up to four 32-column chunks, most of them
+// belonging to the other sequence of the tile) and by 32-line-per-instruction row stores.  Changes:
+//   * slot layout: a tile holds G = 128 / slot sequences, slot = 32 / 64 / 128 rows (the power of two >= S), each
+//     loaded with its own TMA box [slot x 64] (the rows past S are the next sequence's data or zero fill: finite,
+//     masked).  A softmax warp (32 rows) then belongs to ONE sequence and touches only that sequence's
+//     ceil(S/32) column chunks — vision (S = 50): 2 chunks per warp instead of 2-4, text (S = 77): 1-3;
+//   * one pass when a warp needs <= 2 chunks: S stays in registers between max and exp (one TMEM read, no re-mask);
+//     masks are per-lane bit sets built once per kernel (only a key-padding mask refreshes them per tile) and
+//     chunks that are fully visible take a mask-free path;
+//   * the output tile is staged (bf16, 128B-swizzled) in the V buffer, which is free once P.V has retired, and
+//     leaves with one TMA bulk store per sequence (box [S x 64]) instead of 8 x 32-line STG.128 per warp; the
+//     next tile's V load waits for that store to have read the buffer (bar_vfree).
+// =====================================================================================================
+struct AttParams2 {
+  int64_t total_rows;   // n_seq * seq_len
+  int64_t n_seq;
+  int seq_len;          // S
+  int slot;             // rows reserved per sequence inside a tile: 32, 64 or 128
+  int group;            // G = 128 / slot sequences per tile
+  int heads;
+  int64_t seq_tiles;    // ceil(n_seq / G)
+  int causal;
+  const int32_t* key_mask;  // [n_seq, S] or nullptr
+};
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+               "r"(z)
+               : "memory");
+}
+
+// exp2 of one 32-column chunk held in registers (masked entries are -inf -> 0), accumulate the row sum, write P (bf16)
+__device__ __forceinline__ void softmax_chunk_to_p(const uint32_t (&v)[32], float mx_s, float& sum, uint32_t p_taddr) {
+  constexpr float kLog2e = 1.4426950408889634f;
+#pragma unroll
+  for (int hv = 0; hv < 2; ++hv) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float e0 = fast_exp2(fmaf(__uint_as_float(v[16 * hv + 2 * c]), kLog2e, -mx_s));
+      const float e1 = fast_exp2(fmaf(__uint_as_float(v[16 * hv + 2 * c + 1]), kLog2e, -mx_s));
+      sum += e0 + e1;
+      pk[c] = pack_bf16x2(e0, e1);
+    }
+    tmem_st8(p_taddr + 8 * hv, pk);
+  }
+}
+
+// masked entries -> -inf (skipped when the whole warp sees every column of the chunk)
+__device__ __forceinline__ void apply_mask(uint32_t (&v)[32], uint32_t vm) {
+  if (!__all_sync(0xffffffffu, vm == 0xffffffffu)) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (!((vm >> c) & 1u)) v[c] = 0xff800000u;  // -inf
+  }
+}
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float mx) {
+#pragma unroll
+  for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
+  return mx;
+}
+
+template <int CTAS>
+__global__ void __launch_bounds__(kAttThreads, CTAS)
+attention_kernel(const __grid_constant__ CUtensorMap tmLoad, const __grid_constant__ CUtensorMap tmStore,
+                 const AttParams2 p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_raw_u32 = smem_u32(smem_raw);
+  const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStageBytes;
+  const uint32_t bar_qk = bar_base, bar_v = bar_base + 8;
+  const uint32_t bar_s = bar_base + 16, bar_p = bar_base + 24, bar_o = bar_base + 32, bar_e = bar_base + 40;
+  const uint32_t bar_vfree = bar_base + 48;
+  const uint32_t tmem_slot = bar_base + 56;
+  const uint32_t sq = smem_base, sk = smem_base + kTileBytes, sv = smem_base + 2 * kTileBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int D = p.heads * kHeadDim;
+  const int S = p.seq_len, G = p.group, slot = p.slot;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmLoad);
+    tma_prefetch_desc(&tmStore);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_e, 128);
+    mbar_init(bar_vfree, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<1>(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base =
+      *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
+
+  const int64_t num_tiles = p.seq_tiles * p.heads;
+
+  if (warp == 4) {
+    // ===================== TMA producer + MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S = Q K^T, both K-major
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // O = P V, V is MN-major
+      const uint32_t slot_bytes = static_cast<uint32_t>(slot) * 128u;
+      auto issue_qk = [&](int64_t tile) {
+        const int64_t st = tile / p.heads;
+        const int h = (int)(tile - st * p.heads);
+        mbar_arrive_expect_tx(bar_qk, 2 * kTileBytes);
+        for (int g = 0; g < G; ++g) {
+          const int32_t row = (int32_t)((st * G + g) * S);  // past the last sequence: zero fill
+          tma_load_2d(sq + g * slot_bytes, &tmLoad, bar_qk, h * kHeadDim, row);
+          tma_load_2d(sk + g * slot_bytes, &tmLoad, bar_qk, D + h * kHeadDim, row);
+        }
+      };
+      auto issue_v = [&](int64_t tile) {
+        const int64_t st = tile / p.heads;
+        const int h = (int)(tile - st * p.heads);
+        mbar_arrive_expect_tx(bar_v, kTileBytes);
+        for (int g = 0; g < G; ++g)
+          tma_load_2d(sv + g * slot_bytes, &tmLoad, bar_v, 2 * D + h * kHeadDim, (int32_t)((st * G + g) * S));
+      };
+      int64_t tile = blockIdx.x;
+      if (tile < num_tiles) { issue_qk(tile); issue_v(tile); }
+      uint32_t it = 0;
+      const uint64_t qdesc = make_smem_desc_sw128(sq, 1024, 16);
+      const uint64_t kdesc = make_smem_desc_sw128(sk, 1024, 16);
+      for (; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t par = it & 1u;
+        const int64_t next = tile + gridDim.x;
+        mbar_wait(bar_qk, par);
+        if (it > 0) mbar_wait(bar_e, par ^ 1u);  // previous tile's O (aliases S) has been read out
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss<1>(tmem_base + kColS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit<1>(bar_s);
+        if (it > 0) {                            // the previous tile's output store has read the V buffer
+          mbar_wait(bar_vfree, par ^ 1u);
+          issue_v(tile);
+        }
+        mbar_wait(bar_s, par);                   // MMA 1 retired: Q/K buffers are free
+        if (next < num_tiles) issue_qk(next);
+        mbar_wait(bar_p, par);                   // softmax warps published P in TMEM
+        mbar_wait(bar_v, par);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // V tile [128 keys][64 dh]: advancing 16 keys (one UMMA K) = 16 rows of 128 B
+          const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, 1024, 1024);
+          umma_ts(tmem_base + kColO, tmem_base + kColP + k * 8, vdesc, idesc_o, k != 0 ? 1u : 0u);
+        }
+        umma_commit<1>(bar_o);
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue (thread == tile row) =====================
+    const int r = threadIdx.x;                    // 0..127 == TMEM lane == tile row
+    const int g = (warp * 32) / slot;             // the sequence slot this WARP belongs to
+    const int r_in = r - g * slot;                // row inside the sequence
+    const int w_in = (warp * 32 - g * slot) >> 5; // 32-row block of this warp inside its slot
+    const int ct0 = (g * slot) >> 5;              // first 32-column chunk of the slot inside the tile
+    int nch = (S + 31) >> 5;                      // chunks the sequence occupies
+    if (p.causal) nch = min(nch, w_in + 1);       // causal: nothing right of the warp's own diagonal chunk
+    if (w_in * 32 >= S) nch = 0;                  // the whole warp is padding
+    // per-lane visibility bit sets of the slot's chunks (static per thread: sequence end + causal diagonal)
+    uint32_t sm[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int hi = min(min(S, p.causal ? r_in + 1 : S) - 32 * c, 32);
+      sm[c] = (r_in < S && hi > 0) ? (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) : 0u;
+    }
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    uint32_t it = 0;
+    const int ntiles = (int)num_tiles;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int st = tile / p.heads;
+      const int h = tile - st * p.heads;
+      const int64_t seq = (int64_t)st * G + g;
+
+      // visibility bits of slot chunk c for this lane's row: static part & (rarely) the key-padding mask of the tile
+      auto vis = [&](int c) -> uint32_t {
+        uint32_t m = c == 0 ? sm[0] : (c == 1 ? sm[1] : (c == 2 ? sm[2] : sm[3]));
+        if (p.key_mask != nullptr) {
+          const int j = 32 * c + lane;
+          const bool kv = (j < S) && (seq < p.n_seq) && (p.key_mask[seq * S + j] != 0);
+          m &= __ballot_sync(0xffffffffu, kv);
+        }
+        return m;
+      };
+
+      mbar_wait(bar_s, it & 1u);
+      tc_fence_after();
+
+      // The LAST chunk a warp needs is the only one that can be partially visible without a key-padding mask
+      // (sequence end / causal diagonal): it is masked once and kept in registers.  Earlier chunks are read twice
+      // (max, then exp) — a TMEM load costs no ALU work, and they are mask-free unless padded keys exist.
+      float sum = 0.f;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c + 1 < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_base + kColS + 32 * (ct0 + c), v);
+        tmem_ld_wait();
+        apply_mask(v, vis(c));
+        mx = chunk_max(v, mx);
+      }
+      uint32_t last[32];
+      if (nch >= 1) {
+        tmem_ld32(lane_base + kColS + 32 * (ct0 + nch - 1), last);
+        tmem_ld_wait();
+        apply_mask(last, vis(nch - 1));
+        mx = chunk_max(last, mx);
+      }
+      const float mx_s = (mx == -INFINITY) ? 0.f : mx * kLog2e;
+      // P chunk ct overwrites S columns 16 ct .. 16 ct + 15 (= S chunk ct / 2 <= ct): in increasing ct order every
+      // S chunk is still intact when it is re-read
+#pragma unroll 1
+      for (int ct = 0; ct < 4; ++ct) {
+        const uint32_t pt = lane_base + kColP + 16 * ct;
+        const int c = ct - ct0;
+        if (c >= 0 && c + 1 < nch) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + kColS + 32 * ct, v);
+          tmem_ld_wait();
+          apply_mask(v, vis(c));
+          softmax_chunk_to_p(v, mx_s, sum, pt);
+        } else if (c >= 0 && c + 1 == nch) {
+          softmax_chunk_to_p(last, mx_s, sum, pt);
+        } else {
+          tmem_st16_zero(pt);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+
+      // epilogue: O / rowsum -> bf16 -> V buffer (swizzled like a TMA box) -> one bulk store per sequence
+      mbar_wait(bar_o, it & 1u);
+      tc_fence_after();
+      const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+      const uint32_t my_row = sv + static_cast<uint32_t>(r) * 128u;
+      const int sw = r & 7;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t v[32];
+        tmem_ld32(lane_base + kColO + 32 * j, v);
+        tmem_ld_wait();
+        if (j == 1) {  // O fully read: the next tile's S = Q K^T may overwrite these columns
+          tc_fence_before();
+          mbar_arrive(bar_e);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t u0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
+          const uint32_t u1 = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
+          const uint32_t u2 = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
+          const uint32_t u3 = pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (((4 * j + q) ^ sw) << 4)), "r"(u0),
+                       "r"(u1), "r"(u2), "r"(u3)
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) {
+        for (int gg = 0; gg < G; ++gg) {
+          const int64_t sq_idx = (int64_t)st * G + gg;
+          if (sq_idx < p.n_seq)
+            tma_store_2d(&tmStore, sv + static_cast<uint32_t>(gg * slot) * 128u, h * kHeadDim, (int32_t)(sq_idx * S));
+        }
+        tma_store_commit();
+        tma_store_wait_read();   // the V buffer may be refilled
+        mbar_arrive(bar_vfree);
+      }
+    }
+    if (threadIdx.x == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<1>(tmem_base, kTmemCols);
+}
+
 }  // namespace
 
 int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int heads, bool causal,
@@ -289,31 +586,62 @@ int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int h
   PLIP_REQUIRE(heads > 0 && heads <= 16, "attention: bad head count %d", heads);
   static unsigned long long configured = 0;
   static int grid_cap = 0;
+  static int use_v1 = 0, ctas = kAttCtasPerSm;
   if (first_use_on_device(configured)) {
-    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kAttSmem));
+    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kAttSmem));
+    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kAttSmem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    grid_cap = kAttCtasPerSm * sms;
+    const char* v = getenv("PLIP_ATT_V1");  // A/B switch for the round-1 kernel (removed once v2 is validated)
+    use_v1 = (v != nullptr && v[0] == '1') ? 1 : 0;
+    const char* c = getenv("PLIP_ATT_CTAS");  // 3 = 128 registers per thread (no spills), 4 = 96
+    if (c != nullptr && c[0] == '3' && !use_v1) ctas = 3;
+    grid_cap = ctas * sms;
   }
   const int D = heads * kHeadDim;
   const int64_t rows = n_seq * seq_len;
-  CUtensorMap tm;
-  if (int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D * 2, 128, 64)) return rc;
-  AttParams p;
+  PLIP_REQUIRE(rows + 128 < 0x7fffffff, "attention: too many token rows");
+  if (use_v1) {
+    CUtensorMap tm;
+    if (int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D * 2, 128, 64)) return rc;
+    AttParams p;
+    p.total_rows = rows;
+    p.seq_len = seq_len;
+    p.group = 128 / seq_len;
+    p.rows_per_tile = p.group * seq_len;
+    p.heads = heads;
+    p.seq_tiles = (n_seq + p.group - 1) / p.group;
+    p.causal = causal ? 1 : 0;
+    p.key_mask = key_mask;
+    p.out = out;
+    const int64_t tiles = p.seq_tiles * heads;
+    const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
+    PLIP_CUDA_CHECK(launch_kernel(attention_kernel_v1, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tm, p));
+    ++g_launch_count;
+    return 0;
+  }
+  AttParams2 p;
   p.total_rows = rows;
+  p.n_seq = n_seq;
   p.seq_len = seq_len;
-  p.group = 128 / seq_len;
-  p.rows_per_tile = p.group * seq_len;
+  p.slot = seq_len <= 32 ? 32 : (seq_len <= 64 ? 64 : 128);
+  p.group = 128 / p.slot;
   p.heads = heads;
   p.seq_tiles = (n_seq + p.group - 1) / p.group;
   p.causal = causal ? 1 : 0;
   p.key_mask = key_mask;
-  p.out = out;
+  CUtensorMap tmL, tmS;
+  if (int rc = make_tmap_bf16_2d(&tmL, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D * 2, (uint32_t)p.slot, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmS, out, (uint64_t)rows, (uint64_t)D, (uint64_t)D * 2, (uint32_t)seq_len, 64)) return rc;
   const int64_t tiles = p.seq_tiles * heads;
   const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
-  PLIP_CUDA_CHECK(launch_pdl(attention_kernel, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tm, p));
+  if (ctas == 3) PLIP_CUDA_CHECK(launch_kernel(attention_kernel<3>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
+  else PLIP_CUDA_CHECK(launch_kernel(attention_kernel<4>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
   ++g_launch_count;
   return 0;
 }

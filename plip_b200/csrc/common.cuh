@@ -79,33 +79,20 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 #ifdef __CUDACC__
 
 // ---------------------------------------------------------------------------
-// Programmatic dependent launch: every kernel of the forward pass is launched with
-// programmaticStreamSerialization, runs its prologue (barrier init, TMEM allocation, descriptor
-// prefetch) while the previous kernel drains, and calls pdl_wait() before its first global access.
+// Kernel launch helper (cluster dimension as a launch attribute).  Programmatic dependent launch was tried in
+// round 1 and measured again in round 2 (200 full steps each way: 19.55 ms with, 19.38 ms without): no gain on this
+// launch sequence, so the griddepcontrol instructions and the PLIP_PDL switch were removed.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
-// PLIP_PDL=1 enables programmatic dependent launch (off by default: see DESIGN.md §4.5).
-bool pdl_enabled();
-
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                              unsigned cluster_x, Args... args) {
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 unsigned cluster_x, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   int na = 0;
-  if (pdl_enabled()) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
   if (cluster_x > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = cluster_x;

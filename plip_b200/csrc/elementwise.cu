@@ -28,8 +28,6 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 template <int FMT>
 __global__ void __launch_bounds__(kEwThreads) im2col_kernel(const void* __restrict__ pixels,
                                                             __nv_bfloat16* __restrict__ out, int64_t n) {
-  pdl_wait();
-  pdl_launch_dependents();
   constexpr int kX8 = kImage / 8;  // 28 groups of 8 pixels per image row
   const int64_t total = (FMT == PLIP_PIX_U8_NHWC) ? n * kImage * kX8 : n * 3 * kImage * kX8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -92,8 +90,6 @@ __global__ void __launch_bounds__(kEwThreads) layernorm_kernel(const float* __re
                                                                const float* __restrict__ beta,
                                                                float* __restrict__ out_f32,
                                                                __nv_bfloat16* __restrict__ out_bf16) {
-  pdl_wait();
-  pdl_launch_dependents();
   constexpr int V = D / 128;  // float4 per lane
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -145,8 +141,6 @@ template <int D>
 __global__ void __launch_bounds__(kEwThreads) rowstats_cast_kernel(const float* __restrict__ x, int64_t rows,
                                                                    __nv_bfloat16* __restrict__ xb,
                                                                    float2* __restrict__ stats) {
-  pdl_wait();
-  pdl_launch_dependents();
   constexpr int V = D / 128;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -181,8 +175,6 @@ __global__ void __launch_bounds__(kEwThreads) text_embed_kernel(const IdT* __res
                                                                 const float* __restrict__ tok,
                                                                 const float* __restrict__ pos,
                                                                 float* __restrict__ x) {
-  pdl_wait();
-  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -208,8 +200,6 @@ template <typename IdT>
 __global__ void __launch_bounds__(kEwThreads) eos_row_kernel(const IdT* __restrict__ ids, int64_t n,
                                                              int seq_len, int ids_stride, int eos_id,
                                                              int32_t* __restrict__ row_index) {
-  pdl_wait();
-  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -230,8 +220,6 @@ template <typename IdT>
 __global__ void __launch_bounds__(kEwThreads) mask_to_i32_kernel(const IdT* __restrict__ m, int64_t count,
                                                                  int seq_len, int stride,
                                                                  int32_t* __restrict__ out) {
-  pdl_wait();
-  pdl_launch_dependents();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
        i += (int64_t)gridDim.x * blockDim.x)
     out[i] = m[(i / seq_len) * stride + (i % seq_len)] != 0 ? 1 : 0;
@@ -241,8 +229,6 @@ __global__ void __launch_bounds__(kEwThreads) mask_to_i32_kernel(const IdT* __re
 __global__ void __launch_bounds__(kEwThreads) cls_rows_kernel(const float* __restrict__ cls,
                                                               const float* __restrict__ pos, int64_t n,
                                                               float* __restrict__ x) {
-  pdl_wait();
-  pdl_launch_dependents();
   constexpr int V = kVisDim / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * V;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -258,8 +244,6 @@ __global__ void __launch_bounds__(kEwThreads) cls_rows_kernel(const float* __res
 // x[r] /= sqrt(sum x[r]^2): _get_vector_norm, no epsilon (TF:57-65,923-924). One warp per row.
 __global__ void __launch_bounds__(kEwThreads) l2_normalize_kernel(float* __restrict__ x, int64_t rows,
                                                                   int dim) {
-  pdl_wait();
-  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -288,9 +272,9 @@ int launch_im2col(const void* pixels, int fmt, int64_t n, __nv_bfloat16* out, cu
   const int64_t items = (fmt == PLIP_PIX_U8_NHWC ? 1 : 3) * n * kImage * (kImage / 8);
   const int grid = grid_for(items, kEwThreads);
   switch (fmt) {
-    case PLIP_PIX_F32_NCHW: PLIP_CUDA_CHECK(launch_pdl(im2col_kernel<PLIP_PIX_F32_NCHW>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
-    case PLIP_PIX_BF16_NCHW: PLIP_CUDA_CHECK(launch_pdl(im2col_kernel<PLIP_PIX_BF16_NCHW>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
-    case PLIP_PIX_U8_NHWC: PLIP_CUDA_CHECK(launch_pdl(im2col_kernel<PLIP_PIX_U8_NHWC>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
+    case PLIP_PIX_F32_NCHW: PLIP_CUDA_CHECK(launch_kernel(im2col_kernel<PLIP_PIX_F32_NCHW>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
+    case PLIP_PIX_BF16_NCHW: PLIP_CUDA_CHECK(launch_kernel(im2col_kernel<PLIP_PIX_BF16_NCHW>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
+    case PLIP_PIX_U8_NHWC: PLIP_CUDA_CHECK(launch_kernel(im2col_kernel<PLIP_PIX_U8_NHWC>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
     default: set_last_error("im2col: unknown pixel format %d", fmt); return -2;
   }
   PLIP_CUDA_CHECK(cudaGetLastError());
@@ -305,9 +289,9 @@ int launch_layernorm(const float* x, const int32_t* row_index, int64_t in_row_st
   PLIP_REQUIRE(in_row_stride % 4 == 0, "layernorm: row stride must be a multiple of 4 floats");
   const int grid = grid_for(rows, kEwThreads / 32);
   if (dim == kVisDim)
-    PLIP_CUDA_CHECK(launch_pdl(layernorm_kernel<kVisDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16));
+    PLIP_CUDA_CHECK(launch_kernel(layernorm_kernel<kVisDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16));
   else if (dim == kTxtDim)
-    PLIP_CUDA_CHECK(launch_pdl(layernorm_kernel<kTxtDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16));
+    PLIP_CUDA_CHECK(launch_kernel(layernorm_kernel<kTxtDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16));
   else {
     set_last_error("layernorm: unsupported dim %d (768 or 512)", dim);
     return -2;
@@ -321,9 +305,9 @@ int launch_rowstats_cast(const float* x, int64_t rows, int dim, __nv_bfloat16* x
   PLIP_REQUIRE(rows > 0, "rowstats_cast: rows must be positive");
   const int grid = grid_for(rows, kEwThreads / 32);
   if (dim == kVisDim)
-    PLIP_CUDA_CHECK(launch_pdl(rowstats_cast_kernel<kVisDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, rows, xb, stats));
+    PLIP_CUDA_CHECK(launch_kernel(rowstats_cast_kernel<kVisDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, rows, xb, stats));
   else if (dim == kTxtDim)
-    PLIP_CUDA_CHECK(launch_pdl(rowstats_cast_kernel<kTxtDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, rows, xb, stats));
+    PLIP_CUDA_CHECK(launch_kernel(rowstats_cast_kernel<kTxtDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, rows, xb, stats));
   else {
     set_last_error("rowstats_cast: unsupported dim %d", dim);
     return -2;
@@ -340,11 +324,11 @@ int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, in
   const int grid = grid_for(n * seq_len, kEwThreads / 32);
   const int grid2 = grid_for(n, kEwThreads / 32);
   if (ids_dtype == PLIP_IDS_I64) {
-    PLIP_CUDA_CHECK(launch_pdl(text_embed_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, ids_stride, tok, pos, x));
-    PLIP_CUDA_CHECK(launch_pdl(eos_row_kernel<long long>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, ids_stride, eos_id, eos_rows));
+    PLIP_CUDA_CHECK(launch_kernel(text_embed_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, ids_stride, tok, pos, x));
+    PLIP_CUDA_CHECK(launch_kernel(eos_row_kernel<long long>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, ids_stride, eos_id, eos_rows));
   } else if (ids_dtype == PLIP_IDS_I32) {
-    PLIP_CUDA_CHECK(launch_pdl(text_embed_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, ids_stride, tok, pos, x));
-    PLIP_CUDA_CHECK(launch_pdl(eos_row_kernel<int>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, ids_stride, eos_id, eos_rows));
+    PLIP_CUDA_CHECK(launch_kernel(text_embed_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, ids_stride, tok, pos, x));
+    PLIP_CUDA_CHECK(launch_kernel(eos_row_kernel<int>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, ids_stride, eos_id, eos_rows));
   } else {
     set_last_error("text_embed: unknown ids dtype %d", ids_dtype);
     return -2;
@@ -358,16 +342,16 @@ int launch_mask_to_i32(const void* mask, int dtype, int64_t count, int seq_len, 
                        cudaStream_t st) {
   const int grid = grid_for(count, kEwThreads);
   if (dtype == PLIP_IDS_I64)
-    PLIP_CUDA_CHECK(launch_pdl(mask_to_i32_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(mask), count, seq_len, stride, out));
+    PLIP_CUDA_CHECK(launch_kernel(mask_to_i32_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(mask), count, seq_len, stride, out));
   else
-    PLIP_CUDA_CHECK(launch_pdl(mask_to_i32_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(mask), count, seq_len, stride, out));
+    PLIP_CUDA_CHECK(launch_kernel(mask_to_i32_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(mask), count, seq_len, stride, out));
   PLIP_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return 0;
 }
 
 int launch_cls_rows(const float* cls, const float* pos, int64_t n, float* x, cudaStream_t st) {
-  PLIP_CUDA_CHECK(launch_pdl(cls_rows_kernel, dim3(grid_for(n * (kVisDim / 4), kEwThreads)), dim3(kEwThreads), 0, st, 1, cls, pos, n, x));
+  PLIP_CUDA_CHECK(launch_kernel(cls_rows_kernel, dim3(grid_for(n * (kVisDim / 4), kEwThreads)), dim3(kEwThreads), 0, st, 1, cls, pos, n, x));
   PLIP_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return 0;
@@ -375,7 +359,7 @@ int launch_cls_rows(const float* cls, const float* pos, int64_t n, float* x, cud
 
 int launch_l2_normalize(float* x, int64_t rows, int dim, cudaStream_t st) {
   PLIP_REQUIRE(rows > 0 && dim > 0, "l2_normalize: bad shape");
-  PLIP_CUDA_CHECK(launch_pdl(l2_normalize_kernel, dim3(grid_for(rows, kEwThreads / 32)), dim3(kEwThreads), 0, st, 1, x, rows, dim));
+  PLIP_CUDA_CHECK(launch_kernel(l2_normalize_kernel, dim3(grid_for(rows, kEwThreads / 32)), dim3(kEwThreads), 0, st, 1, x, rows, dim));
   PLIP_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return 0;

@@ -333,8 +333,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base =
       *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
-  pdl_wait();               // the producer of A / the residual stream has completed
-  pdl_launch_dependents();  // let the next kernel's prologue fill SMs as they free up
 
   const int num_n_blk = p.N / BN;
   const int num_m_blk = (p.M + BM * CG - 1) / (BM * CG);
@@ -553,7 +551,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   int groups = max_groups;
   if (groups > num_tiles) groups = num_tiles;
 
-  PLIP_CUDA_CHECK(launch_pdl(kern, dim3(groups * CG), dim3(kThreads), C::SMEM_BYTES, stream, CG, tmA, tmB, tmC, p));
+  PLIP_CUDA_CHECK(launch_kernel(kern, dim3(groups * CG), dim3(kThreads), C::SMEM_BYTES, stream, CG, tmA, tmB, tmC, p));
   ++g_launch_count;
   return 0;
 }
@@ -600,6 +598,9 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     if (g.N % 192 == 0) bn = 192;
     else if (g.N == 512) bn = 128;  // text out_proj: 86.5 vs 91.8 us (exp14)
   }
+  static const int env_bn_fc2 = env_int("PLIP_GEMM_BN_FC2", 0);  // experiment: N tile of the long-K residual GEMM (fc2)
+  if (!g.force_bn && !env_bn && env_bn_fc2 && cg == 2 && g.epi == EPI_BIAS_RESID_F32 && g.K > 1024 && g.N % env_bn_fc2 == 0)
+    bn = env_bn_fc2;
   if (g.N % bn != 0) bn = 128;
   PLIP_REQUIRE((cg == 1 || cg == 2) && (bn == 128 || bn == 256 || (bn == 192 && cg == 2)),
                "launch_gemm: bad config cg=%d bn=%d", cg, bn);

@@ -175,8 +175,6 @@ __global__ void __launch_bounds__(kRsThreads) resize_crop_kernel(const uint8_t* 
                                                                  uint8_t* __restrict__ tiles, const ResizeBatch batch,
                                                                  int64_t first_image) {
   extern __shared__ __align__(16) uint8_t rs_smem[];
-  pdl_wait();
-  pdl_launch_dependents();
   const ResizeImg& im = batch.img[blockIdx.y];
   const int row0 = blockIdx.x * kRsRowsPerCta;  // first output row of this CTA
   const AxisFilter fh = make_axis(im.w, im.new_w), fv = make_axis(im.h, im.new_h);
@@ -367,7 +365,7 @@ int launch_resize_crop(const uint8_t* src, size_t src_bytes, const plip_resize_d
       if (int rc = plan_image(d[base + i], (long long)(base + i), src_bytes, b.img[i], need)) return rc;
       smem = need > smem ? need : smem;
     }
-    PLIP_CUDA_CHECK(launch_pdl(resize_crop_kernel, dim3(kImage / kRsRowsPerCta, cnt), dim3(kRsThreads), smem, st, 1,
+    PLIP_CUDA_CHECK(launch_kernel(resize_crop_kernel, dim3(kImage / kRsRowsPerCta, cnt), dim3(kRsThreads), smem, st, 1,
                                src, (uint64_t)src_bytes, tiles, b, base));
     ++g_launch_count;
   }

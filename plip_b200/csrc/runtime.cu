@@ -22,14 +22,6 @@ void set_last_error(const char* fmt, ...) {
 
 const char* get_last_error() { return g_last_error; }
 
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* v = getenv("PLIP_PDL");
-    return v != nullptr && v[0] == '1';
-  }();
-  return on;
-}
-
 // cuTensorMapEncodeTiled is a driver-API symbol; resolve it through the runtime so the library
 // does not link against libcuda.so (absent on the build box).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

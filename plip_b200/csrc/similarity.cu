@@ -25,8 +25,6 @@ similarity_kernel(const float* __restrict__ A, int64_t n, const float* __restric
   __shared__ float Bs[TK][TN + 4];
   __shared__ float inv_a[TM], inv_b[TN];
 
-  pdl_wait();
-  pdl_launch_dependents();
   const int t = threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.y * TM;
   const int64_t col0 = (int64_t)blockIdx.x * TN;
@@ -108,8 +106,6 @@ similarity_topk_kernel(const float* __restrict__ Q, int64_t n, const float* __re
   __shared__ float ls[4][kTopkMax];
   __shared__ int li[4][kTopkMax];
   __shared__ float red[4];
-  pdl_wait();
-  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x;
 
@@ -217,8 +213,6 @@ similarity_topk_tiled_kernel(const float* __restrict__ Q, int64_t n, const float
   L.i = reinterpret_cast<int*>(L.v + TM * kTopkMax);
   __shared__ unsigned last_flag;
 
-  pdl_wait();
-  pdl_launch_dependents();
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int64_t row0 = (int64_t)blockIdx.x * TM;
   const int lr = t >> 2, lk = (t & 3) * 4, ty = t >> 4, tx = t & 15;
@@ -356,7 +350,7 @@ int launch_similarity(const float* a, int64_t n, const float* b, int64_t m, floa
   const int64_t gy = (n + TM - 1) / TM, gx = (m + TN - 1) / TN;
   PLIP_REQUIRE(gy <= 65535, "similarity: n=%lld too large for one launch (chunk rows)", (long long)n);
   dim3 grid((unsigned)gx, (unsigned)gy);
-  PLIP_CUDA_CHECK(launch_pdl(similarity_kernel, grid, dim3(kSimThreads), 0, st, 1, a, n, b, m, (int)kProj, scale,
+  PLIP_CUDA_CHECK(launch_kernel(similarity_kernel, grid, dim3(kSimThreads), 0, st, 1, a, n, b, m, (int)kProj, scale,
                              norm_a ? 1 : 0, norm_b ? 1 : 0, out, ldo));
   ++g_launch_count;
   return 0;
@@ -369,7 +363,7 @@ int launch_similarity_topk(const float* q, int64_t n, const float* s, int64_t m,
   PLIP_REQUIRE(n <= 0x7fffffff && m <= 0x7fffffff, "similarity_topk: operand too large");
   if (n * m < (int64_t)1 << 16) {
     // tiny problems (e.g. a handful of class prompts): one CTA per query streaming the space
-    PLIP_CUDA_CHECK(launch_pdl(similarity_topk_kernel, dim3((unsigned)n), dim3(kTopkThreads), 0, st, 1, q, n, s, m,
+    PLIP_CUDA_CHECK(launch_kernel(similarity_topk_kernel, dim3((unsigned)n), dim3(kTopkThreads), 0, st, 1, q, n, s, m,
                                (int)kProj, scale, norm_q ? 1 : 0, norm_s ? 1 : 0, k, idx, val));
     ++g_launch_count;
     return 0;
@@ -421,7 +415,7 @@ int launch_similarity_topk(const float* q, int64_t n, const float* s, int64_t m,
     tickets = reinterpret_cast<unsigned*>(scratch_i + ent);
     PLIP_CUDA_CHECK(cudaMemsetAsync(tickets, 0, (size_t)row_tiles * 4, st));
     dim3 grid((unsigned)row_tiles, (unsigned)splits);
-    PLIP_CUDA_CHECK(launch_pdl(similarity_topk_tiled_kernel, grid, dim3(kTkThreads), smem, st, 1, q, n, s, m, (int)kProj,
+    PLIP_CUDA_CHECK(launch_kernel(similarity_topk_tiled_kernel, grid, dim3(kTkThreads), smem, st, 1, q, n, s, m, (int)kProj,
                                scale, norm_q ? 1 : 0, norm_s ? 1 : 0, k, tiles_per_split, scratch_v, scratch_i, tickets,
                                idx, val));
     PLIP_CUDA_CHECK(cudaEventRecord(sc.ev, st));
@@ -429,7 +423,7 @@ int launch_similarity_topk(const float* q, int64_t n, const float* s, int64_t m,
     return 0;
   }
   dim3 grid((unsigned)row_tiles, (unsigned)splits);
-  PLIP_CUDA_CHECK(launch_pdl(similarity_topk_tiled_kernel, grid, dim3(kTkThreads), smem, st, 1, q, n, s, m, (int)kProj,
+  PLIP_CUDA_CHECK(launch_kernel(similarity_topk_tiled_kernel, grid, dim3(kTkThreads), smem, st, 1, q, n, s, m, (int)kProj,
                              scale, norm_q ? 1 : 0, norm_s ? 1 : 0, k, tiles_per_split, scratch_v, scratch_i, tickets,
                              idx, val));
   ++g_launch_count;

@@ -115,15 +115,18 @@ def test_outlier_weights_towers_vs_oracle(outlier_sd):
         h = eng.hidden_states("vision", px[:4].cuda(), nl).cpu()
         d = (h - hid[nl]).abs()
         big = hid[nl].abs() > 20
-        assert (d[big] / hid[nl].abs()[big]).max().item() < 2e-3, nl    # massive channels: relative
+        assert (d[big] / hid[nl].abs()[big]).max().item() < 2.5e-3, nl  # massive channels: relative (emulated contract: 1.2e-3)
         assert d[~big].max().item() < 0.12 and d[~big].mean().item() < 8e-3, (nl, d[~big].max().item(), d[~big].mean().item())
     thid = []
     O.text_transformer(outlier_sd, ids[:4], mask[:4], hidden=thid)
     th = eng.hidden_states("text", ids[:4].cuda(), 12, attention_mask=mask[:4].cuda()).cpu()
     td = (th - thid[12]).abs()
     tbig = thid[12].abs() > 20
-    assert (td[tbig] / thid[12].abs()[tbig]).max().item() < 2e-3
-    assert td[~tbig].max().item() < 0.15 and td[~tbig].mean().item() < 1e-2, (td[~tbig].max().item(), td[~tbig].mean().item())
+    # bounds = 2x what the CPU emulation of the bf16-operand contract gives on these inputs (tools/precision_study.py:
+    # massive channels 5.8e-3 relative, others 0.05 max / 8.3e-3 mean) — the massive channels' token-dependent part
+    # is itself a K = 2048 bf16 dot product with 20x scaled weights
+    assert (td[tbig] / thid[12].abs()[tbig]).max().item() < 1.2e-2
+    assert td[~tbig].max().item() < 0.15 and td[~tbig].mean().item() < 1.7e-2, (td[~tbig].max().item(), td[~tbig].mean().item())
     out = model(input_ids=ids.cuda(), pixel_values=px.cuda(), attention_mask=mask.cuda())
     ref = O.clip_forward(outlier_sd, ids, px, mask)
     ci = (1 - O.cosine(out.image_embeds.cpu(), ref["image_embeds"])).max().item()

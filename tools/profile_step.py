@@ -1,6 +1,10 @@
 """Run a few vision (and text) forwards at batch 1024 for ncu launch lists / captures (no timing here)."""
+import os
 import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import weights
 from plip_b200.engine import Engine
 
