@@ -466,9 +466,10 @@ def run_ours(args):
     torch.set_num_threads(max(1, min(32, usable_cores() // max(1, ws))))
     peaks = _peaks()
 
+    configs = args.config.split(",")
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        sd, cpu = cpu_baseline_sample(args.config)
+        sd, cpu = cpu_baseline_sample(configs[0])
         torch.set_num_threads(max(1, min(32, usable_cores() // max(1, ws))))
     else:
         from plip_b200 import synthetic
@@ -477,16 +478,21 @@ def run_ours(args):
     from plip_b200 import distributed as D
     from plip_b200._lib import lib
     from plip_b200.modeling import PlipCLIPModel
-    model = PlipCLIPModel(sd, device=dev, max_micro_batch=PAIRS)
+    model = PlipCLIPModel(sd, device=dev, max_micro_batch=PAIRS, operand_dtype=args.operands)
     ctx = {"args": args, "rank": rank, "ws": ws, "dev": dev, "peaks": peaks, "cpu": cpu, "sd": sd, "model": model,
            "eng": model.engine, "L": lib(), "sh": D.ShardedCLIP.from_engine(model.engine), "timer": Timer(dev, ws)}
-    if args.config == "pairs":
-        return bench_pairs(ctx)
-    if args.config == "cfg3":
-        return bench_cfg3(ctx)
-    if args.config == "cfg4":
-        return bench_cfg4(ctx)
-    return bench_cfg5(ctx)
+    # several comma-separated configs share one process (one weight upload): one JSON line each — the driver's
+    # default invocation names a single config and gets a single line
+    rc = 0
+    steps_arg = args.steps
+    for name in configs:
+        args.config = name
+        args.steps = steps_arg if steps_arg is not None else {"pairs": 10, "cfg3": 5, "cfg4": 3, "cfg5": 2}[name]
+        if name != configs[0]:
+            ctx["cpu"] = None
+        rc |= {"pairs": bench_pairs, "cfg3": bench_cfg3, "cfg4": bench_cfg4, "cfg5": bench_cfg5}[name](ctx)
+        torch.cuda.empty_cache()
+    return rc
 
 
 def traffic_json():
@@ -500,7 +506,7 @@ def emit(ctx, value, unit, metric, ms_per_step, steps, scaling, clocks, e2e, lau
     args, ws = ctx["args"], ctx["ws"]
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": ws, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": config_dict(args.config, ws), "clocks": clocks, "e2e": e2e,
+            "dtype": args.operands, "data": "synthetic", "config": config_dict(args.config, ws), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": ctx["cpu"], "extra": extra}
     print(json.dumps(line), flush=True)
 
@@ -868,15 +874,22 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="pairs", choices=sorted(WORKLOADS))
+    ap.add_argument("--config", default="pairs", help="pairs (default) | cfg3 | cfg4 | cfg5, or a comma-separated list")
     ap.add_argument("--tiles", type=int, default=0, help="cfg4 / cfg5: override the total tile count (default 100k / 1M)")
     ap.add_argument("--queries", type=int, default=0, help="cfg5: override the query count (default 10k)")
+    ap.add_argument("--operands", default="bf16", choices=["bf16", "fp16"],
+                    help="16-bit format of the GEMM / attention operands (default bf16 = BASELINE.json's dtype)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-context", action="store_true", help="skip the stock-PyTorch-on-GPU context measurement")
     ap.add_argument("--quick", action="store_true", help="skip the extras (kernels alone, product-API extras, context)")
     args = ap.parse_args()
-    if args.steps is None:
-        args.steps = {"pairs": 10, "cfg3": 5, "cfg4": 3, "cfg5": 2}[args.config]
+    for c in args.config.split(","):
+        if c not in WORKLOADS:
+            ap.error(f"unknown config {c!r}")
+    if args.impl == "reference":
+        args.config = args.config.split(",")[0]
+        if args.steps is None:
+            args.steps = 5
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rc = run_reference(args) if args.impl == "reference" else run_ours(args)
     if torch.distributed.is_available() and torch.distributed.is_initialized():

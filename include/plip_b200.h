@@ -32,7 +32,7 @@ extern "C" {
 
 #define PLIP_API __attribute__((visibility("default")))
 
-#define PLIP_B200_ABI_VERSION 4  /* 3: + plip_resize_crop_u8; 4: + plip_profile_* */
+#define PLIP_B200_ABI_VERSION 4  /* 3: + plip_resize_crop_u8; 4: + plip_profile_*, plip_create_ex (operand format) */
 
 /* Model constants (TF:configuration_clip.py:47-64,97-109,160-161). */
 #define PLIP_IMAGE_SIZE 224
@@ -52,6 +52,13 @@ enum plip_pixel_format {
 
 enum plip_id_dtype { PLIP_IDS_I32 = 0, PLIP_IDS_I64 = 1 };
 
+/* 16-bit format of every GEMM / attention OPERAND (packed weights, activations between kernels).  Accumulation, the
+ * residual stream, LayerNorm statistics, softmax and the similarity head are float32 in both.  tcgen05 kind::f16
+ * runs both at the same rate.  BF16 is the default (BASELINE.json's dtype).  FP16 keeps 3 more significand bits:
+ * end-to-end |dlogits_per_image| is 6-8x smaller (profiles/r2_precision_study.md) — the reference's own OpenAI-clip
+ * flavour runs fp16 weights on the GPU (scripts/extract_embedding.py:94-97) — at the price of a 65504 range. */
+enum plip_operand_format { PLIP_OPERAND_BF16 = 0, PLIP_OPERAND_FP16 = 1 };
+
 /* ---- errors / version ---------------------------------------------------------------------- */
 PLIP_API const char* plip_last_error(void);
 PLIP_API int plip_abi_version(void);
@@ -67,7 +74,7 @@ typedef struct plip_tensor_info {
   char name[96];    /* HuggingFace-style name, e.g. "vision_model.encoder.layers.0.mlp.fc1.weight" */
   uint64_t offset;  /* byte offset inside the blob (256-byte aligned) */
   uint64_t numel;
-  int32_t dtype;    /* 0 = float32, 1 = bfloat16 */
+  int32_t dtype;    /* 0 = float32, 1 = 16-bit operand (bfloat16, or IEEE half for a PLIP_OPERAND_FP16 engine) */
   int32_t rows;     /* logical 2-D shape (rows x cols), cols == 1 for vectors */
   int32_t cols;
   int32_t fused;    /* 0 = plain copy of the named tensor.
@@ -89,10 +96,19 @@ PLIP_API uint64_t plip_weights_blob_bytes(void);
  * are looped in micro-batches.  Device memory: blob + plip_workspace_bytes(max_micro_batch). */
 PLIP_API int plip_create(const void* host_blob, uint64_t blob_bytes, float logit_scale_exp, int device,
                          int max_micro_batch, plip_engine_t** out);
+/* Same with an explicit operand format: the 16-bit entries of host_blob must have been packed in that format. */
+PLIP_API int plip_create_ex(const void* host_blob, uint64_t blob_bytes, float logit_scale_exp, int device,
+                            int max_micro_batch, int operand_format, plip_engine_t** out);
 PLIP_API int plip_destroy(plip_engine_t* e);
 PLIP_API uint64_t plip_workspace_bytes(int max_micro_batch);
 PLIP_API float plip_logit_scale_exp(const plip_engine_t* e);
 PLIP_API int plip_max_micro_batch(const plip_engine_t* e);
+PLIP_API int plip_operand_format(const plip_engine_t* e);
+/* Pooled position of a caption WITHOUT an eos token (49407).  0 (default): position 0, as transformers does for
+ * configs with eos_token_id == 49407 (TF:571-584: argmax of an all-zero match vector).  1: first position of the
+ * largest id, as legacy configs (eos_token_id == 2 — what openai/clip-vit-base-patch32 ships) and OpenAI clip's
+ * text.argmax(-1) do (TF:564-570).  Captions that contain an eos are pooled at its first position either way. */
+PLIP_API int plip_set_text_pooling(plip_engine_t* e, int no_eos_argmax);
 
 /* ---- the hot path -------------------------------------------------------------------------- */
 /* Vision tower + visual_projection: replaces CLIPModel.get_image_features (TF:829-863, called at
@@ -187,6 +203,8 @@ PLIP_API int plip_profile_enable(plip_engine_t* e, int on);
 PLIP_API int plip_profile_read(plip_engine_t* e, plip_kernel_time_t* out, int cap, int* count);
 
 /* ---- per-kernel test hooks (used by tests/ only; stream-ordered, device pointers) ------------ */
+/* The handle-free hooks below interpret / produce 16-bit data in the format set here (default PLIP_OPERAND_BF16). */
+PLIP_API int plip_dbg_set_operand_format(int operand_format);
 /* epilogue: 0 bias->bf16, 1 bias+QuickGELU->bf16, 2 x_f32 += acc+bias (optionally also xb_out bf16 copy +
  * stats_out [M,8,2] row statistics), 3 patch scatter + pos, 4 plain f32, 5/6 = 0/1 with the LayerNorm fold
  * (colsum [N], stats_in [M,8,2] with n_partials valid slots). */

@@ -63,6 +63,10 @@ SIGNATURES = {
     "plip_weights_tensor_info": (_i, [_i, C.POINTER(TensorInfo)]),
     "plip_weights_blob_bytes": (_u64, []),
     "plip_create": (_i, [_vp, _u64, _f, _i, _i, C.POINTER(_vp)]),
+    "plip_create_ex": (_i, [_vp, _u64, _f, _i, _i, _i, C.POINTER(_vp)]),
+    "plip_operand_format": (_i, [_vp]),
+    "plip_set_text_pooling": (_i, [_vp, _i]),
+    "plip_dbg_set_operand_format": (_i, [_i]),
     "plip_destroy": (_i, [_vp]),
     "plip_workspace_bytes": (_u64, [_i]),
     "plip_logit_scale_exp": (_f, [_vp]),

@@ -320,17 +320,20 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 
 // exp2 of one 32-column chunk held in registers (masked entries are -inf -> 0), accumulate the row sum, write P (bf16)
-__device__ __forceinline__ void softmax_chunk_to_p(const uint32_t (&v)[32], float mx_s, float& sum, uint32_t p_taddr) {
+template <bool F16>
+__device__ __forceinline__ void softmax_chunk_to_p(const uint32_t (&v)[32], float mx_s, float2& sum2, uint32_t p_taddr) {
   constexpr float kLog2e = 1.4426950408889634f;
 #pragma unroll
   for (int hv = 0; hv < 2; ++hv) {
     uint32_t pk[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
+      // (a packed FFMA2 / FADD2 version of this loop costs 70 more registers than the 96 available at 4 CTAs per SM)
       const float e0 = fast_exp2(fmaf(__uint_as_float(v[16 * hv + 2 * c]), kLog2e, -mx_s));
       const float e1 = fast_exp2(fmaf(__uint_as_float(v[16 * hv + 2 * c + 1]), kLog2e, -mx_s));
-      sum += e0 + e1;
-      pk[c] = pack_bf16x2(e0, e1);
+      sum2.x += e0;
+      sum2.y += e1;
+      pk[c] = pack_op2<F16>(e0, e1);
     }
     tmem_st8(p_taddr + 8 * hv, pk);
   }
@@ -350,7 +353,7 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float mx) {
   return mx;
 }
 
-template <int CTAS>
+template <int CTAS, bool F16>
 __global__ void __launch_bounds__(kAttThreads, CTAS)
 attention_kernel(const __grid_constant__ CUtensorMap tmLoad, const __grid_constant__ CUtensorMap tmStore,
                  const AttParams2 p) {
@@ -393,8 +396,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmLoad, const __grid_consta
   if (warp == 4) {
     // ===================== TMA producer + MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S = Q K^T, both K-major
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // O = P V, V is MN-major
+      constexpr uint32_t idesc_s = make_idesc_op(128, 128, 0, 0, F16);  // S = Q K^T, both K-major
+      constexpr uint32_t idesc_o = make_idesc_op(128, 64, 0, 1, F16);   // O = P V, V is MN-major
       const uint32_t slot_bytes = static_cast<uint32_t>(slot) * 128u;
       auto issue_qk = [&](int64_t tile) {
         const int64_t st = tile / p.heads;
@@ -490,7 +493,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmLoad, const __grid_consta
       // The LAST chunk a warp needs is the only one that can be partially visible without a key-padding mask
       // (sequence end / causal diagonal): it is masked once and kept in registers.  Earlier chunks are read twice
       // (max, then exp) — a TMEM load costs no ALU work, and they are mask-free unless padded keys exist.
-      float sum = 0.f;
+      float2 sum2 = make_float2(0.f, 0.f);
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c + 1 < nch; ++c) {
@@ -519,9 +522,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmLoad, const __grid_consta
           tmem_ld32(lane_base + kColS + 32 * ct, v);
           tmem_ld_wait();
           apply_mask(v, vis(c));
-          softmax_chunk_to_p(v, mx_s, sum, pt);
+          softmax_chunk_to_p<F16>(v, mx_s, sum2, pt);
         } else if (c >= 0 && c + 1 == nch) {
-          softmax_chunk_to_p(last, mx_s, sum, pt);
+          softmax_chunk_to_p<F16>(last, mx_s, sum2, pt);
         } else {
           tmem_st16_zero(pt);
         }
@@ -533,7 +536,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmLoad, const __grid_consta
       // epilogue: O / rowsum -> bf16 -> V buffer (swizzled like a TMA box) -> one bulk store per sequence
       mbar_wait(bar_o, it & 1u);
       tc_fence_after();
+      const float sum = sum2.x + sum2.y;
       const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+      const float2 inv2 = make_float2(inv, inv);
       const uint32_t my_row = sv + static_cast<uint32_t>(r) * 128u;
       const int sw = r & 7;
 #pragma unroll
@@ -547,10 +552,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmLoad, const __grid_consta
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint32_t u0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
-          const uint32_t u1 = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
-          const uint32_t u2 = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
-          const uint32_t u3 = pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
+          uint32_t u[4];
+#pragma unroll
+          for (int w2 = 0; w2 < 4; ++w2) {
+            const float2 o = __fmul2_rn(make_float2(__uint_as_float(v[8 * q + 2 * w2]), __uint_as_float(v[8 * q + 2 * w2 + 1])), inv2);
+            u[w2] = pack_op2<F16>(o.x, o.y);
+          }
+          const uint32_t u0 = u[0], u1 = u[1], u2 = u[2], u3 = u[3];
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (((4 * j + q) ^ sw) << 4)), "r"(u0),
                        "r"(u1), "r"(u2), "r"(u3)
                        : "memory");
@@ -580,7 +588,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmLoad, const __grid_consta
 }  // namespace
 
 int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int heads, bool causal,
-                     const int32_t* key_mask, __nv_bfloat16* out, cudaStream_t st) {
+                     const int32_t* key_mask, __nv_bfloat16* out, int f16, cudaStream_t st) {
   PLIP_REQUIRE(n_seq > 0 && seq_len > 0 && seq_len <= 128, "attention: bad shape n_seq=%lld seq_len=%d",
                (long long)n_seq, seq_len);
   PLIP_REQUIRE(heads > 0 && heads <= 16, "attention: bad head count %d", heads);
@@ -588,10 +596,9 @@ int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int h
   static int grid_cap = 0;
   static int use_v1 = 0, ctas = kAttCtasPerSm;
   if (first_use_on_device(configured)) {
-    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kAttSmem));
-    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kAttSmem));
+    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmem));
+    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmem));
+    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmem));
     PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kAttSmem));
     int dev = 0, sms = 148;
@@ -606,6 +613,7 @@ int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int h
   const int D = heads * kHeadDim;
   const int64_t rows = n_seq * seq_len;
   PLIP_REQUIRE(rows + 128 < 0x7fffffff, "attention: too many token rows");
+  PLIP_REQUIRE(!(f16 && (use_v1 || ctas == 3)), "attention: the fp16 operand format runs on the default kernel only");
   if (use_v1) {
     CUtensorMap tm;
     if (int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D * 2, 128, 64)) return rc;
@@ -640,8 +648,9 @@ int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int h
   if (int rc = make_tmap_bf16_2d(&tmS, out, (uint64_t)rows, (uint64_t)D, (uint64_t)D * 2, (uint32_t)seq_len, 64)) return rc;
   const int64_t tiles = p.seq_tiles * heads;
   const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
-  if (ctas == 3) PLIP_CUDA_CHECK(launch_kernel(attention_kernel<3>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
-  else PLIP_CUDA_CHECK(launch_kernel(attention_kernel<4>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
+  if (ctas == 3) PLIP_CUDA_CHECK(launch_kernel(attention_kernel<3, false>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
+  else if (f16) PLIP_CUDA_CHECK(launch_kernel(attention_kernel<4, true>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
+  else PLIP_CUDA_CHECK(launch_kernel(attention_kernel<4, false>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
   ++g_launch_count;
   return 0;
 }

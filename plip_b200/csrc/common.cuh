@@ -8,6 +8,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -313,6 +314,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
+// Same with IEEE half operands (a_format = b_format = 0): kind::f16 runs fp16 and bf16 at the same rate.  The
+// engine's "fp16" operand format (plip_create_ex) keeps 11 instead of 8 significand bits in every GEMM /
+// attention operand: end-to-end |dlogits| 6-8x smaller (profiles/r2_precision_study.md), range 65504.
+__host__ __device__ constexpr uint32_t make_idesc_op(int m, int n, int a_mn_major, int b_mn_major, bool f16) {
+  return f16 ? (make_idesc_bf16(m, n, a_mn_major, b_mn_major) & ~((1u << 7) | (1u << 10)))
+             : make_idesc_bf16(m, n, a_mn_major, b_mn_major);
+}
 
 // ---------------------------------------------------------------------------
 // tcgen05: MMA issue / commit
@@ -414,6 +422,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// two fp32 -> one 32-bit word of the engine's 16-bit operand format
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi) {
+  if constexpr (F16) return pack_f16x2(lo, hi);
+  else return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ uint32_t pack_op2_rt(float lo, float hi, int f16) {  // memory-bound kernels: runtime format
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
 // QuickGELU: x * sigmoid(1.702 x)   (TF:activations.py:117-123)
 // sigmoid(y) = 0.5 * (1 + tanh(y / 2)): one MUFU op (tanh.approx.f32, max rel. error 2^-11) instead of
 // ex2 + rcp.  The fc1 epilogue is MUFU-bound (ncu r1: 128x256 tile = 4096 MUFU cycles per SM sub-partition
@@ -423,6 +444,17 @@ __device__ __forceinline__ float quick_gelu(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
   const float h = 0.5f * x;
   return fmaf(h, t, h);
+}
+// Two elements at once with Blackwell's packed fp32 pipe (FMUL2 / FFMA2: one issue slot, two results).  The epilogues
+// and the softmax are FMA-pipe / issue bound next to the tensor pipe (ncu r2b: text fc1 epilogue paces the MMAs at
+// K = 512), so every scalar FFMA pair that becomes one FFMA2 shortens the co-critical path.
+__device__ __forceinline__ float2 quick_gelu2(float2 x) {
+  const float2 a = __fmul2_rn(x, make_float2(0.851f, 0.851f));
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(a.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(a.y));
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(h, t, h);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -10,12 +10,12 @@ namespace {
 
 constexpr int kEwThreads = 256;
 
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int f16) {
   uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]);
-  u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]);
-  u.w = pack_bf16x2(f[6], f[7]);
+  u.x = pack_op2_rt(f[0], f[1], f16);
+  u.y = pack_op2_rt(f[2], f[3], f16);
+  u.z = pack_op2_rt(f[4], f[5], f16);
+  u.w = pack_op2_rt(f[6], f[7], f16);
   return u;
 }
 
@@ -27,7 +27,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 template <int FMT>
 __global__ void __launch_bounds__(kEwThreads) im2col_kernel(const void* __restrict__ pixels,
-                                                            __nv_bfloat16* __restrict__ out, int64_t n) {
+                                                            __nv_bfloat16* __restrict__ out, int64_t n, int f16) {
   constexpr int kX8 = kImage / 8;  // 28 groups of 8 pixels per image row
   const int64_t total = (FMT == PLIP_PIX_U8_NHWC) ? n * kImage * kX8 : n * 3 * kImage * kX8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kEwThreads) im2col_kernel(const void* __restri
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = (bytes[j * 3 + c] * (1.0f / 255.0f) - mean[c]) * istd[c];
-        *reinterpret_cast<uint4*>(dst + c * 1024) = pack8(f);
+        *reinterpret_cast<uint4*>(dst + c * 1024) = pack8(f, f16);
       }
     } else {
       const int c = (int)(r % 3);
@@ -67,10 +67,21 @@ __global__ void __launch_bounds__(kEwThreads) im2col_kernel(const void* __restri
         const float4* s4 = reinterpret_cast<const float4*>(static_cast<const float*>(pixels) + src_off);
         const float4 a = __ldg(s4), bq = __ldg(s4 + 1);
         const float f[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
-        *reinterpret_cast<uint4*>(dst) = pack8(f);
-      } else {  // bf16 NCHW: straight 16-byte copy
-        *reinterpret_cast<uint4*>(dst) =
-            __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(pixels) + src_off));
+        *reinterpret_cast<uint4*>(dst) = pack8(f, f16);
+      } else {  // bf16 NCHW: straight 16-byte copy (re-rounded to half for the fp16 operand format)
+        uint4 w = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(pixels) + src_off));
+        if (f16) {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 t = __bfloat1622float2(h2[j]);
+            f[2 * j] = t.x;
+            f[2 * j + 1] = t.y;
+          }
+          w = pack8(f, 1);
+        }
+        *reinterpret_cast<uint4*>(dst) = w;
       }
     }
   }
@@ -89,7 +100,7 @@ __global__ void __launch_bounds__(kEwThreads) layernorm_kernel(const float* __re
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta,
                                                                float* __restrict__ out_f32,
-                                                               __nv_bfloat16* __restrict__ out_bf16) {
+                                                               __nv_bfloat16* __restrict__ out_bf16, int f16) {
   constexpr int V = D / 128;  // float4 per lane
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -124,8 +135,8 @@ __global__ void __launch_bounds__(kEwThreads) layernorm_kernel(const float* __re
       if (out_f32) reinterpret_cast<float4*>(out_f32 + r * D)[lane + 32 * j] = y;
       if (out_bf16) {
         uint2 u;
-        u.x = pack_bf16x2(y.x, y.y);
-        u.y = pack_bf16x2(y.z, y.w);
+        u.x = pack_op2_rt(y.x, y.y, f16);
+        u.y = pack_op2_rt(y.z, y.w, f16);
         reinterpret_cast<uint2*>(out_bf16 + r * D)[lane + 32 * j] = u;
       }
     }
@@ -140,7 +151,7 @@ __global__ void __launch_bounds__(kEwThreads) layernorm_kernel(const float* __re
 template <int D>
 __global__ void __launch_bounds__(kEwThreads) rowstats_cast_kernel(const float* __restrict__ x, int64_t rows,
                                                                    __nv_bfloat16* __restrict__ xb,
-                                                                   float2* __restrict__ stats) {
+                                                                   float2* __restrict__ stats, int f16) {
   constexpr int V = D / 128;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -154,8 +165,8 @@ __global__ void __launch_bounds__(kEwThreads) rowstats_cast_kernel(const float* 
       s1 += (v.x + v.y) + (v.z + v.w);
       s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
       uint2 u;
-      u.x = pack_bf16x2(v.x, v.y);
-      u.y = pack_bf16x2(v.z, v.w);
+      u.x = pack_op2_rt(v.x, v.y, f16);
+      u.y = pack_op2_rt(v.z, v.w, f16);
       reinterpret_cast<uint2*>(xb + r * D)[lane + 32 * j] = u;
     }
     s1 = warp_sum(s1);
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(kEwThreads) text_embed_kernel(const IdT* __res
 template <typename IdT>
 __global__ void __launch_bounds__(kEwThreads) eos_row_kernel(const IdT* __restrict__ ids, int64_t n,
                                                              int seq_len, int ids_stride, int eos_id,
-                                                             int32_t* __restrict__ row_index) {
+                                                             int no_eos_argmax, int32_t* __restrict__ row_index) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -211,7 +222,28 @@ __global__ void __launch_bounds__(kEwThreads) eos_row_kernel(const IdT* __restri
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (m) first = t0 + __ffs(m) - 1;
     }
-    if (lane == 0) row_index[b] = (int32_t)(b * seq_len + (first == seq_len ? 0 : first));
+    if (first == seq_len) {
+      // no eos in the row.  HF with eos_token_id == 49407 pools position 0 here ((ids == eos).argmax() of all zeros,
+      // TF:571-584); legacy configs (eos_token_id == 2, what openai/clip-vit-base-patch32 ships) and OpenAI clip pool
+      // the first position of the largest id (TF:564-570) — selected by plip_set_text_pooling.
+      first = 0;
+      if (no_eos_argmax) {
+        long long best = -(1ll << 62);
+        int best_t = 0;
+        for (int t = lane; t < seq_len; t += 32) {
+          const long long v = (long long)ids[b * ids_stride + t];
+          if (v > best) { best = v; best_t = t; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const long long ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+          if (ov > best || (ov == best && ot < best_t)) { best = ov; best_t = ot; }
+        }
+        first = best_t;
+      }
+    }
+    if (lane == 0) row_index[b] = (int32_t)(b * seq_len + first);
   }
 }
 
@@ -266,15 +298,15 @@ inline int grid_for(int64_t work_items, int per_block) {
 
 }  // namespace
 
-int launch_im2col(const void* pixels, int fmt, int64_t n, __nv_bfloat16* out, cudaStream_t st) {
+int launch_im2col(const void* pixels, int fmt, int64_t n, __nv_bfloat16* out, int f16, cudaStream_t st) {
   PLIP_REQUIRE(n > 0, "im2col: n must be positive");
   PLIP_REQUIRE((reinterpret_cast<uintptr_t>(pixels) & 15) == 0, "im2col: pixels must be 16-byte aligned");
   const int64_t items = (fmt == PLIP_PIX_U8_NHWC ? 1 : 3) * n * kImage * (kImage / 8);
   const int grid = grid_for(items, kEwThreads);
   switch (fmt) {
-    case PLIP_PIX_F32_NCHW: PLIP_CUDA_CHECK(launch_kernel(im2col_kernel<PLIP_PIX_F32_NCHW>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
-    case PLIP_PIX_BF16_NCHW: PLIP_CUDA_CHECK(launch_kernel(im2col_kernel<PLIP_PIX_BF16_NCHW>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
-    case PLIP_PIX_U8_NHWC: PLIP_CUDA_CHECK(launch_kernel(im2col_kernel<PLIP_PIX_U8_NHWC>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n)); break;
+    case PLIP_PIX_F32_NCHW: PLIP_CUDA_CHECK(launch_kernel(im2col_kernel<PLIP_PIX_F32_NCHW>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n, f16)); break;
+    case PLIP_PIX_BF16_NCHW: PLIP_CUDA_CHECK(launch_kernel(im2col_kernel<PLIP_PIX_BF16_NCHW>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n, f16)); break;
+    case PLIP_PIX_U8_NHWC: PLIP_CUDA_CHECK(launch_kernel(im2col_kernel<PLIP_PIX_U8_NHWC>, dim3(grid), dim3(kEwThreads), 0, st, 1, pixels, out, n, f16)); break;
     default: set_last_error("im2col: unknown pixel format %d", fmt); return -2;
   }
   PLIP_CUDA_CHECK(cudaGetLastError());
@@ -283,15 +315,15 @@ int launch_im2col(const void* pixels, int fmt, int64_t n, __nv_bfloat16* out, cu
 }
 
 int launch_layernorm(const float* x, const int32_t* row_index, int64_t in_row_stride, int64_t rows, int dim,
-                     const float* gamma, const float* beta, float* out_f32, __nv_bfloat16* out_bf16,
+                     const float* gamma, const float* beta, float* out_f32, __nv_bfloat16* out_bf16, int f16,
                      cudaStream_t st) {
   PLIP_REQUIRE(rows > 0, "layernorm: rows must be positive");
   PLIP_REQUIRE(in_row_stride % 4 == 0, "layernorm: row stride must be a multiple of 4 floats");
   const int grid = grid_for(rows, kEwThreads / 32);
   if (dim == kVisDim)
-    PLIP_CUDA_CHECK(launch_kernel(layernorm_kernel<kVisDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16));
+    PLIP_CUDA_CHECK(launch_kernel(layernorm_kernel<kVisDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16, f16));
   else if (dim == kTxtDim)
-    PLIP_CUDA_CHECK(launch_kernel(layernorm_kernel<kTxtDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16));
+    PLIP_CUDA_CHECK(launch_kernel(layernorm_kernel<kTxtDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, row_index, in_row_stride, rows, gamma, beta, out_f32, out_bf16, f16));
   else {
     set_last_error("layernorm: unsupported dim %d (768 or 512)", dim);
     return -2;
@@ -301,13 +333,13 @@ int launch_layernorm(const float* x, const int32_t* row_index, int64_t in_row_st
   return 0;
 }
 
-int launch_rowstats_cast(const float* x, int64_t rows, int dim, __nv_bfloat16* xb, float2* stats, cudaStream_t st) {
+int launch_rowstats_cast(const float* x, int64_t rows, int dim, __nv_bfloat16* xb, float2* stats, int f16, cudaStream_t st) {
   PLIP_REQUIRE(rows > 0, "rowstats_cast: rows must be positive");
   const int grid = grid_for(rows, kEwThreads / 32);
   if (dim == kVisDim)
-    PLIP_CUDA_CHECK(launch_kernel(rowstats_cast_kernel<kVisDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, rows, xb, stats));
+    PLIP_CUDA_CHECK(launch_kernel(rowstats_cast_kernel<kVisDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, rows, xb, stats, f16));
   else if (dim == kTxtDim)
-    PLIP_CUDA_CHECK(launch_kernel(rowstats_cast_kernel<kTxtDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, rows, xb, stats));
+    PLIP_CUDA_CHECK(launch_kernel(rowstats_cast_kernel<kTxtDim>, dim3(grid), dim3(kEwThreads), 0, st, 1, x, rows, xb, stats, f16));
   else {
     set_last_error("rowstats_cast: unsupported dim %d", dim);
     return -2;
@@ -317,7 +349,7 @@ int launch_rowstats_cast(const float* x, int64_t rows, int dim, __nv_bfloat16* x
 }
 
 int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, int ids_stride, const float* tok,
-                      const float* pos, float* x, int32_t* eos_rows, int eos_id, cudaStream_t st) {
+                      const float* pos, float* x, int32_t* eos_rows, int eos_id, int no_eos_argmax, cudaStream_t st) {
   PLIP_REQUIRE(ids_stride >= seq_len, "text_embed: ids row stride %d < seq_len %d", ids_stride, seq_len);
   PLIP_REQUIRE(n > 0 && seq_len > 0 && seq_len <= kTxtSeq, "text_embed: bad shape n=%lld seq_len=%d",
                (long long)n, seq_len);
@@ -325,10 +357,10 @@ int launch_text_embed(const void* ids, int ids_dtype, int64_t n, int seq_len, in
   const int grid2 = grid_for(n, kEwThreads / 32);
   if (ids_dtype == PLIP_IDS_I64) {
     PLIP_CUDA_CHECK(launch_kernel(text_embed_kernel<long long>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, ids_stride, tok, pos, x));
-    PLIP_CUDA_CHECK(launch_kernel(eos_row_kernel<long long>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, ids_stride, eos_id, eos_rows));
+    PLIP_CUDA_CHECK(launch_kernel(eos_row_kernel<long long>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const long long*>(ids), n, seq_len, ids_stride, eos_id, no_eos_argmax, eos_rows));
   } else if (ids_dtype == PLIP_IDS_I32) {
     PLIP_CUDA_CHECK(launch_kernel(text_embed_kernel<int>, dim3(grid), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, ids_stride, tok, pos, x));
-    PLIP_CUDA_CHECK(launch_kernel(eos_row_kernel<int>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, ids_stride, eos_id, eos_rows));
+    PLIP_CUDA_CHECK(launch_kernel(eos_row_kernel<int>, dim3(grid2), dim3(kEwThreads), 0, st, 1, static_cast<const int*>(ids), n, seq_len, ids_stride, eos_id, no_eos_argmax, eos_rows));
   } else {
     set_last_error("text_embed: unknown ids dtype %d", ids_dtype);
     return -2;

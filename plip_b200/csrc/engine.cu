@@ -121,6 +121,8 @@ using namespace plip;
 struct plip_engine {
   int device = 0;
   int max_mb = 0;
+  int text_pool_argmax = 0;  // rows without an eos token: 0 = position 0 (HF, eos_token_id 49407), 1 = argmax of the ids (legacy / OpenAI)
+  int f16 = 0;  // 16-bit operand format of the packed GEMM weights and of every activation operand: 0 bf16, 1 IEEE half
   float logit_scale_exp = 1.f;
   uint8_t* d_blob = nullptr;
   // vision
@@ -253,7 +255,7 @@ int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int
   const double dM = (double)M, dD = (double)D, dF = (double)FF;
   {
     ProfScope ps(e, st, PK_ROWSTATS, 0, dM * dD * 6 + dM * 8);
-    if (int rc = launch_rowstats_cast(e->X, M, D, e->Xn, e->stats, st)) return rc;
+    if (int rc = launch_rowstats_cast(e->X, M, D, e->Xn, e->stats, e->f16, st)) return rc;
   }
   // algorithmic HBM bytes per launch: operands read once, outputs written once
   const double b_qkv = dM * dD * 2 + 3 * dD * dD * 2 + dM * 3 * dD * 2;
@@ -267,6 +269,7 @@ int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int
     const LayerW& w = L[l];
     // x = x + out_proj(attn(LN1(x)))                                     TF:modeling_clip.py:370-377
     GemmArgs g;
+    g.f16 = e->f16;
     g.A = e->Xn; g.lda = D; g.W = w.wqkv; g.ldw = D; g.M = (int)M; g.N = 3 * D; g.K = D;
     g.bias = w.bqkv; g.colsum = w.sqkv; g.stats_in = e->stats; g.n_partials = np;
     g.out = e->QKV; g.ldo = 3 * D; g.epi = EPI_LN_BIAS_BF16;
@@ -276,9 +279,10 @@ int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int
     }
     {
       ProfScope ps(e, st, PK_ATTN, f_att, b_att);
-      if (int rc = launch_attention(e->QKV, n_seq, S, heads, causal, kmask, e->AO, st)) return rc;
+      if (int rc = launch_attention(e->QKV, n_seq, S, heads, causal, kmask, e->AO, e->f16, st)) return rc;
     }
     g = GemmArgs();
+    g.f16 = e->f16;
     g.A = e->AO; g.lda = D; g.W = w.wo; g.ldw = D; g.M = (int)M; g.N = D; g.K = D;
     g.bias = w.bo; g.out = e->X; g.ldo = D; g.epi = EPI_BIAS_RESID_F32;
     g.xb_out = e->Xn; g.stats_out = e->stats; g.n_tiles_used = &np;
@@ -288,6 +292,7 @@ int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int
     }
     // x = x + fc2(quick_gelu(fc1(LN2(x))))                                TF:modeling_clip.py:379-382
     g = GemmArgs();
+    g.f16 = e->f16;
     g.A = e->Xn; g.lda = D; g.W = w.w1; g.ldw = D; g.M = (int)M; g.N = FF; g.K = D;
     g.bias = w.b1; g.colsum = w.s1; g.stats_in = e->stats; g.n_partials = np;
     g.out = e->H; g.ldo = FF; g.epi = EPI_LN_BIAS_GELU_BF16;
@@ -296,6 +301,7 @@ int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int
       if (int rc = launch_gemm(g, st)) return rc;
     }
     g = GemmArgs();
+    g.f16 = e->f16;
     g.A = e->H; g.lda = FF; g.W = w.w2; g.ldw = FF; g.M = (int)M; g.N = D; g.K = FF;
     g.bias = w.b2; g.out = e->X; g.ldo = D; g.epi = EPI_BIAS_RESID_F32;
     if (l + 1 < num_layers) {  // the last layer's output only feeds the pooled-row LayerNorm (fp32 X)
@@ -315,9 +321,10 @@ int vision_trunk(plip_engine* e, const void* pixels, int fmt, int64_t mb, int nu
   const double dmb = (double)mb;
   {
     ProfScope ps(e, st, PK_IM2COL, 0, dmb * (double)pixel_bytes(fmt) + dmb * kPatches * kPatchK * 2);
-    if (int rc = launch_im2col(pixels, fmt, mb, e->H, st)) return rc;
+    if (int rc = launch_im2col(pixels, fmt, mb, e->H, e->f16, st)) return rc;
   }
   GemmArgs g;
+  g.f16 = e->f16;
   g.A = e->H; g.lda = kPatchK; g.W = e->v_patch_w; g.ldw = kPatchK;
   g.M = (int)(mb * kPatches); g.N = kVisDim; g.K = kPatchK;
   g.out = e->X; g.ldo = kVisDim; g.pos = e->v_pos; g.epi = EPI_PATCH_F32;
@@ -333,7 +340,7 @@ int vision_trunk(plip_engine* e, const void* pixels, int fmt, int64_t mb, int nu
   const int64_t M = mb * kVisSeq;
   {
     ProfScope ps(e, st, PK_LN, 0, (double)M * kVisDim * 8);
-    if (int rc = launch_layernorm(e->X, nullptr, kVisDim, M, kVisDim, e->v_pre_g, e->v_pre_b, e->X, nullptr, st)) return rc;
+    if (int rc = launch_layernorm(e->X, nullptr, kVisDim, M, kVisDim, e->v_pre_g, e->v_pre_b, e->X, nullptr, e->f16, st)) return rc;
   }
   return run_layers(e, e->vis, mb, kVisSeq, kVisDim, kVisFF, kVisHeads, false, nullptr, num_layers, st);
 }
@@ -345,9 +352,10 @@ int vision_forward(plip_engine* e, const void* pixels, int fmt, int64_t mb, floa
   {
     ProfScope ps(e, st, PK_LN, 0, (double)mb * kVisDim * 6);
     if (int rc = launch_layernorm(e->X, nullptr, (int64_t)kVisSeq * kVisDim, mb, kVisDim, e->v_post_g, e->v_post_b,
-                                  nullptr, e->pooled, st)) return rc;
+                                  nullptr, e->pooled, e->f16, st)) return rc;
   }
   GemmArgs g;
+  g.f16 = e->f16;
   g.A = e->pooled; g.lda = kVisDim; g.W = e->v_proj; g.ldw = kVisDim;
   g.M = (int)mb; g.N = kProj; g.K = kVisDim; g.out = out; g.ldo = kProj; g.epi = EPI_F32;
   {
@@ -369,7 +377,7 @@ int text_trunk(plip_engine* e, const void* ids, int ids_dtype, const void* mask,
   e->prof_tower = 1;
   {
     ProfScope ps(e, st, PK_EMBED, 0, (double)mb * S * kTxtDim * 8);
-    if (int rc = launch_text_embed(ids, ids_dtype, mb, S, stride, e->t_tok, e->t_pos, e->X, e->row_idx, kEosId, st)) return rc;
+    if (int rc = launch_text_embed(ids, ids_dtype, mb, S, stride, e->t_tok, e->t_pos, e->X, e->row_idx, kEosId, e->text_pool_argmax, st)) return rc;
   }
   const int32_t* km = nullptr;
   if (mask) {
@@ -387,9 +395,10 @@ int text_forward(plip_engine* e, const void* ids, int ids_dtype, const void* mas
   {
     ProfScope ps(e, st, PK_LN, 0, (double)mb * kTxtDim * 6);
     if (int rc = launch_layernorm(e->X, e->row_idx, kTxtDim, mb, kTxtDim, e->t_fin_g, e->t_fin_b, nullptr,
-                                  e->pooled, st)) return rc;
+                                  e->pooled, e->f16, st)) return rc;
   }
   GemmArgs g;
+  g.f16 = e->f16;
   g.A = e->pooled; g.lda = kTxtDim; g.W = e->t_proj; g.ldw = kTxtDim;
   g.M = (int)mb; g.N = kProj; g.K = kTxtDim; g.out = out; g.ldo = kProj; g.epi = EPI_F32;
   {
@@ -531,7 +540,14 @@ PLIP_API uint64_t plip_workspace_bytes(int max_micro_batch) {
 
 PLIP_API int plip_create(const void* host_blob, uint64_t nbytes, float logit_scale_exp, int device,
                          int max_micro_batch, plip_engine_t** out) {
+  return plip_create_ex(host_blob, nbytes, logit_scale_exp, device, max_micro_batch, PLIP_OPERAND_BF16, out);
+}
+
+PLIP_API int plip_create_ex(const void* host_blob, uint64_t nbytes, float logit_scale_exp, int device,
+                            int max_micro_batch, int operand_format, plip_engine_t** out) {
   PLIP_REQUIRE(out != nullptr && host_blob != nullptr, "plip_create: null argument");
+  PLIP_REQUIRE(operand_format == PLIP_OPERAND_BF16 || operand_format == PLIP_OPERAND_FP16,
+               "plip_create: unknown operand format %d", operand_format);
   PLIP_REQUIRE(nbytes == blob_bytes(), "plip_create: blob is %llu bytes, expected %llu",
                (unsigned long long)nbytes, (unsigned long long)blob_bytes());
   PLIP_REQUIRE(max_micro_batch >= 1 && max_micro_batch <= 8192, "plip_create: max_micro_batch %d out of [1,8192]",
@@ -547,6 +563,7 @@ PLIP_API int plip_create(const void* host_blob, uint64_t nbytes, float logit_sca
   plip_engine* e = new plip_engine();
   e->device = device;
   e->max_mb = max_micro_batch;
+  e->f16 = operand_format == PLIP_OPERAND_FP16 ? 1 : 0;
   e->logit_scale_exp = logit_scale_exp;
   const WsLayout w = ws_layout(max_micro_batch);
   uint8_t* ws = nullptr;
@@ -645,6 +662,12 @@ PLIP_API int plip_profile_read(plip_engine_t* e, plip_kernel_time_t* out, int ca
 
 PLIP_API float plip_logit_scale_exp(const plip_engine_t* e) { return e ? e->logit_scale_exp : 0.f; }
 PLIP_API int plip_max_micro_batch(const plip_engine_t* e) { return e ? e->max_mb : 0; }
+PLIP_API int plip_operand_format(const plip_engine_t* e) { return e ? e->f16 : -1; }
+PLIP_API int plip_set_text_pooling(plip_engine_t* e, int no_eos_argmax) {
+  PLIP_REQUIRE(e != nullptr, "plip_set_text_pooling: null engine");
+  e->text_pool_argmax = no_eos_argmax != 0;
+  return 0;
+}
 
 PLIP_API int plip_encode_images(plip_engine_t* e, const void* pixels_dev, int pixel_format, int64_t n,
                                 float* out_dev, int normalize, void* stream) {
@@ -867,6 +890,14 @@ PLIP_API int plip_dbg_text_bucket_plan(const int32_t* lens_host, int64_t n, int 
 }
 
 // ---- per-kernel test hooks ------------------------------------------------------------------------
+static int g_dbg_f16 = 0;  // operand format the handle-free hooks below run in
+PLIP_API int plip_dbg_set_operand_format(int operand_format) {
+  PLIP_REQUIRE(operand_format == PLIP_OPERAND_BF16 || operand_format == PLIP_OPERAND_FP16,
+               "plip_dbg_set_operand_format: unknown operand format %d", operand_format);
+  g_dbg_f16 = operand_format == PLIP_OPERAND_FP16 ? 1 : 0;
+  return 0;
+}
+
 PLIP_API int plip_dbg_gemm(const void* A_bf16, int lda, const void* W_bf16, int ldw, int M, int N, int K,
                            const float* bias, void* out, int ldo, const float* pos, int epilogue, int cta_group,
                            int block_n, const float* colsum, const float* stats_in, int n_partials, void* xb_out,
@@ -879,28 +910,30 @@ PLIP_API int plip_dbg_gemm(const void* A_bf16, int lda, const void* W_bf16, int 
   g.colsum = colsum; g.stats_in = reinterpret_cast<const float2*>(stats_in); g.n_partials = n_partials;
   g.xb_out = static_cast<__nv_bfloat16*>(xb_out); g.stats_out = reinterpret_cast<float2*>(stats_out);
   g.force_cg = cta_group; g.force_bn = block_n;
+  g.f16 = g_dbg_f16;
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
 PLIP_API int plip_dbg_rowstats_cast(const float* x, int64_t rows, int dim, void* xb_bf16, float* stats, void* stream) {
   return launch_rowstats_cast(x, rows, dim, static_cast<__nv_bfloat16*>(xb_bf16), reinterpret_cast<float2*>(stats),
-                              static_cast<cudaStream_t>(stream));
+                              g_dbg_f16, static_cast<cudaStream_t>(stream));
 }
 
 PLIP_API int plip_dbg_layernorm(const float* x, int64_t rows, int dim, int64_t in_row_stride, const float* gamma,
                                 const float* beta, float* out_f32, void* out_bf16, void* stream) {
   return launch_layernorm(x, nullptr, in_row_stride, rows, dim, gamma, beta, out_f32,
-                          static_cast<__nv_bfloat16*>(out_bf16), static_cast<cudaStream_t>(stream));
+                          static_cast<__nv_bfloat16*>(out_bf16), g_dbg_f16, static_cast<cudaStream_t>(stream));
 }
 
 PLIP_API int plip_dbg_attention(const void* qkv_bf16, int64_t n_seq, int seq_len, int heads, int causal,
                                 const int32_t* key_mask, void* out_bf16, void* stream) {
   return launch_attention(static_cast<const __nv_bfloat16*>(qkv_bf16), n_seq, seq_len, heads, causal != 0, key_mask,
-                          static_cast<__nv_bfloat16*>(out_bf16), static_cast<cudaStream_t>(stream));
+                          static_cast<__nv_bfloat16*>(out_bf16), g_dbg_f16, static_cast<cudaStream_t>(stream));
 }
 
 PLIP_API int plip_dbg_im2col(const void* pixels, int pixel_format, int64_t n, void* out_bf16, void* stream) {
-  return launch_im2col(pixels, pixel_format, n, static_cast<__nv_bfloat16*>(out_bf16), static_cast<cudaStream_t>(stream));
+  return launch_im2col(pixels, pixel_format, n, static_cast<__nv_bfloat16*>(out_bf16), g_dbg_f16,
+                       static_cast<cudaStream_t>(stream));
 }
 
 PLIP_API int plip_dbg_hidden_states(plip_engine_t* e, int tower, const void* input_dev, int input_format,

@@ -39,6 +39,7 @@ struct GemmArgs {
   float2* stats_out = nullptr;       // EPI_BIAS_RESID_F32 (optional): [M, kStatSlots], slot = N-tile index
   int* n_tiles_used = nullptr;       // out (host): number of statistics slots written (2 per N tile)
   int epi = EPI_F32;
+  int f16 = 0;                       // 16-bit operand format of A, W and the bf16-typed outputs: 0 = bfloat16, 1 = IEEE half
   int force_cg = 0;                  // 0 = auto; 1 / 2 = CTA-group size (test hook)
   int force_bn = 0;                  // 0 = auto; 128 / 256 = N tile (test hook)
 };

@@ -92,35 +92,38 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   return v;
 }
 
-// acc (+ bias from the smem bias tile) for 32 consecutive columns of this thread's row.
-// LN_FOLD: rstd * (acc - mean * colsum) + bias', colsum tile stored BN floats after the bias tile pair.
+// acc (+ bias from the smem bias tile) for 32 consecutive columns of this thread's row, as 16 float2 (packed fp32 math).
+// LN_FOLD: rstd * acc + (bias' - (rstd * mean) * colsum)  ==  rstd * (acc - mean * colsum) + bias'; the colsum tile is
+// stored BN floats after the bias tile pair.  `nrm` = -rstd * mean.
 template <bool HAS_BIAS, bool LN_FOLD, int BN>
-__device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, float mean, float rstd,
-                                           float (&f)[32]) {
+__device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, float nrm, float rstd,
+                                           float2 (&f)[16]) {
   uint32_t v[32];
   tmem_ld32(taddr, v);
   tmem_ld_wait();
+  const float2 nrm2 = make_float2(nrm, nrm), rstd2 = make_float2(rstd, rstd);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (HAS_BIAS) b = ld_shared_f4(bias_smem + 16 * i);  // broadcast read
+    const float2 a0 = make_float2(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]));
+    const float2 a1 = make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
     if constexpr (LN_FOLD) {
       const float4 cs = ld_shared_f4(bias_smem + 2 * BN * 4 + 16 * i);
-      f[4 * i + 0] = fmaf(rstd, fmaf(-mean, cs.x, __uint_as_float(v[4 * i + 0])), b.x);
-      f[4 * i + 1] = fmaf(rstd, fmaf(-mean, cs.y, __uint_as_float(v[4 * i + 1])), b.y);
-      f[4 * i + 2] = fmaf(rstd, fmaf(-mean, cs.z, __uint_as_float(v[4 * i + 2])), b.z);
-      f[4 * i + 3] = fmaf(rstd, fmaf(-mean, cs.w, __uint_as_float(v[4 * i + 3])), b.w);
+      f[2 * i + 0] = __ffma2_rn(rstd2, a0, __ffma2_rn(nrm2, make_float2(cs.x, cs.y), make_float2(b.x, b.y)));
+      f[2 * i + 1] = __ffma2_rn(rstd2, a1, __ffma2_rn(nrm2, make_float2(cs.z, cs.w), make_float2(b.z, b.w)));
+    } else if constexpr (HAS_BIAS) {
+      f[2 * i + 0] = __fadd2_rn(a0, make_float2(b.x, b.y));
+      f[2 * i + 1] = __fadd2_rn(a1, make_float2(b.z, b.w));
     } else {
-      f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
-      f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
-      f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
-      f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+      f[2 * i + 0] = a0;
+      f[2 * i + 1] = a1;
     }
   }
 }
 
 // One accumulator tile (this warp's 32 rows x BN columns) -> global memory.
-template <int BN, int EPI>
+template <int BN, int EPI, bool F16>
 __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMap* tmC, uint32_t tmem_row_base,
                                               uint32_t stage_smem,
                                               uint32_t bias_smem, int row_base, int col_base, int n_blk, int half,
@@ -158,26 +161,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
       }
 #pragma unroll
       for (int half2 = 0; half2 < 2; ++half2) {
-        float f[32];
+        float2 f[16];
         load_acc32<HAS_BIAS, LN_FOLD, BN>(tmem_row_base + blk * 64 + half2 * 32, bias_smem + (blk * 64 + half2 * 32) * 4,
                                           mean, rstd, f);
         if (p.dbg >= 2) {
           float a = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a += f[i];
+          for (int i = 0; i < 16; ++i) a += f[i].x + f[i].y;
           if (a == 1.2345e30f) reinterpret_cast<float*>(p.out)[0] = a;
           continue;
         }
         if constexpr (GELU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
+          for (int i = 0; i < 16; ++i) f[i] = quick_gelu2(f[i]);
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int chunk = half2 * 4 + c;
-          st_shared_v4(my_row + ((chunk ^ sw) << 4), pack_bf16x2(f[8 * c + 0], f[8 * c + 1]),
-                       pack_bf16x2(f[8 * c + 2], f[8 * c + 3]), pack_bf16x2(f[8 * c + 4], f[8 * c + 5]),
-                       pack_bf16x2(f[8 * c + 6], f[8 * c + 7]));
+          st_shared_v4(my_row + ((chunk ^ sw) << 4), pack_op2<F16>(f[4 * c + 0].x, f[4 * c + 0].y),
+                       pack_op2<F16>(f[4 * c + 1].x, f[4 * c + 1].y), pack_op2<F16>(f[4 * c + 2].x, f[4 * c + 2].y),
+                       pack_op2<F16>(f[4 * c + 3].x, f[4 * c + 3].y));
         }
       }
       if (p.tma_store) {
@@ -227,12 +230,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
         }
       }
       {
-        float f[32];
+        float2 f[16];
         load_acc32<HAS_BIAS, false, BN>(tmem_row_base + blk * 32, bias_smem + blk * 32 * 4, 0.f, 1.f, f);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          st_shared_v4(my_row + ((c ^ sw) << 4), __float_as_uint(f[4 * c + 0]), __float_as_uint(f[4 * c + 1]),
-                       __float_as_uint(f[4 * c + 2]), __float_as_uint(f[4 * c + 3]));
+          st_shared_v4(my_row + ((c ^ sw) << 4), __float_as_uint(f[2 * c + 0].x), __float_as_uint(f[2 * c + 0].y),
+                       __float_as_uint(f[2 * c + 1].x), __float_as_uint(f[2 * c + 1].y));
       }
       __syncwarp();
 #pragma unroll
@@ -242,16 +245,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
         const int grow = row_base + r;
         if (grow < p.M) {
           if constexpr (EPI == EPI_BIAS_RESID_F32) {
-            const float4 y = make_float4(xr[i].x + v.x, xr[i].y + v.y, xr[i].z + v.z, xr[i].w + v.w);
+            const float2 y01 = __fadd2_rn(make_float2(xr[i].x, xr[i].y), make_float2(v.x, v.y));
+            const float2 y23 = __fadd2_rn(make_float2(xr[i].z, xr[i].w), make_float2(v.z, v.w));
+            const float4 y = make_float4(y01.x, y01.y, y23.x, y23.y);
             *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldo + col) = y;
             if (emit) {
               // bf16 copy (A operand of the next, LayerNorm-folded GEMM) + statistics of the fp32 row
               uint2 u;
-              u.x = pack_bf16x2(y.x, y.y);
-              u.y = pack_bf16x2(y.z, y.w);
+              u.x = pack_op2<F16>(y.x, y.y);
+              u.y = pack_op2<F16>(y.z, y.w);
               *reinterpret_cast<uint2*>(p.xb_out + static_cast<size_t>(grow) * p.ldo + col) = u;
-              st1[i] += (y.x + y.y) + (y.z + y.w);
-              st2[i] += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+              const float2 s = __fadd2_rn(y01, y23);
+              const float2 q = __ffma2_rn(y01, y01, __fmul2_rn(y23, y23));
+              st1[i] += s.x + s.y;
+              st2[i] += q.x + q.y;
             }
           } else if constexpr (EPI == EPI_PATCH_F32) {
             const int b = grow / kPatches;
@@ -285,7 +292,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
   }
 }
 
-template <int CG, int BN, int EPI>
+template <int CG, int BN, int EPI, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
@@ -372,7 +379,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == kWarpMma) {
     // ===================== MMA issuer (leader CTA) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_op(BM * CG, BN, 0, 0, F16);
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
@@ -456,11 +463,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const float inv_k = 1.0f / static_cast<float>(p.K);
         ln_mean = s1 * inv_k;
         ln_rstd = rsqrtf(fmaxf(s2 * inv_k - ln_mean * ln_mean, 0.f) + kLnEps);
+        ln_mean = -ln_rstd * ln_mean;  // the epilogue wants rstd * acc + (bias' + (-rstd * mean) * colsum)
       }
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      epilogue_tile<BN, EPI>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + a * BN * 4, row_base,
+      epilogue_tile<BN, EPI, F16>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + a * BN * 4, row_base,
                              n_blk * BN, n_blk, half, lane, ln_mean, ln_rstd);
       tc_fence_before();
       __syncwarp();
@@ -495,10 +503,10 @@ int num_sms() {
   return n;
 }
 
-template <int CG, int BN, int EPI>
+template <int CG, int BN, int EPI, bool F16>
 int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   using C = Cfg<CG, BN, EPI>;
-  auto kern = gemm_kernel<CG, BN, EPI>;
+  auto kern = gemm_kernel<CG, BN, EPI, F16>;
   static unsigned long long configured = 0;
   static int max_groups = 0;  // co-resident CTAs (CG == 1) or CTA pairs (CG == 2) for this kernel
   if (first_use_on_device(configured)) {
@@ -556,19 +564,23 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   return 0;
 }
 
-template <int CG, int BN>
-int launch_epi(const GemmArgs& g, cudaStream_t stream) {
+template <int CG, int BN, bool F16>
+int launch_epi_fmt(const GemmArgs& g, cudaStream_t stream) {
   switch (g.epi) {
-    case EPI_BIAS_BF16: return launch_inst<CG, BN, EPI_BIAS_BF16>(g, stream);
-    case EPI_BIAS_GELU_BF16: return launch_inst<CG, BN, EPI_BIAS_GELU_BF16>(g, stream);
-    case EPI_BIAS_RESID_F32: return launch_inst<CG, BN, EPI_BIAS_RESID_F32>(g, stream);
-    case EPI_PATCH_F32: return launch_inst<CG, BN, EPI_PATCH_F32>(g, stream);
-    case EPI_F32: return launch_inst<CG, BN, EPI_F32>(g, stream);
-    case EPI_LN_BIAS_BF16: return launch_inst<CG, BN, EPI_LN_BIAS_BF16>(g, stream);
-    case EPI_LN_BIAS_GELU_BF16: return launch_inst<CG, BN, EPI_LN_BIAS_GELU_BF16>(g, stream);
-    case EPI_NULL: return launch_inst<CG, BN, EPI_NULL>(g, stream);
+    case EPI_BIAS_BF16: return launch_inst<CG, BN, EPI_BIAS_BF16, F16>(g, stream);
+    case EPI_BIAS_GELU_BF16: return launch_inst<CG, BN, EPI_BIAS_GELU_BF16, F16>(g, stream);
+    case EPI_BIAS_RESID_F32: return launch_inst<CG, BN, EPI_BIAS_RESID_F32, F16>(g, stream);
+    case EPI_PATCH_F32: return launch_inst<CG, BN, EPI_PATCH_F32, F16>(g, stream);
+    case EPI_F32: return launch_inst<CG, BN, EPI_F32, F16>(g, stream);
+    case EPI_LN_BIAS_BF16: return launch_inst<CG, BN, EPI_LN_BIAS_BF16, F16>(g, stream);
+    case EPI_LN_BIAS_GELU_BF16: return launch_inst<CG, BN, EPI_LN_BIAS_GELU_BF16, F16>(g, stream);
+    case EPI_NULL: return launch_inst<CG, BN, EPI_NULL, F16>(g, stream);
     default: set_last_error("launch_gemm: bad epilogue %d", g.epi); return -2;
   }
+}
+template <int CG, int BN>
+int launch_epi(const GemmArgs& g, cudaStream_t stream) {
+  return g.f16 ? launch_epi_fmt<CG, BN, true>(g, stream) : launch_epi_fmt<CG, BN, false>(g, stream);
 }
 
 }  // namespace

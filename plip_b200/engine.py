@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from ._lib import check, lib
-from .weights import pack_state_dict
+from .weights import operand_format, pack_state_dict
 
 PIX_F32_NCHW, PIX_BF16_NCHW, PIX_U8_NHWC = 0, 1, 2
 IDS_I32, IDS_I64 = 0, 1
@@ -63,7 +63,10 @@ class Engine:
     """One engine per CUDA device: packed bf16/fp32 weights + workspace for ``max_micro_batch``."""
 
     def __init__(self, state_dict: Mapping[str, torch.Tensor], device: Union[int, str, torch.device, None] = None,
-                 max_micro_batch: int = 1024):
+                 max_micro_batch: int = 1024, operand_dtype="bf16"):
+        """``operand_dtype``: 16-bit format of the GEMM / attention operands — ``"bf16"`` (default, BASELINE's dtype) or
+        ``"fp16"`` (same speed, 3 more significand bits: 6-8x smaller end-to-end logits error, 65504 range; what the
+        reference's OpenAI-clip flavour runs on a GPU).  Accumulation / residual stream / softmax are fp32 in both."""
         if not torch.cuda.is_available():
             raise RuntimeError("plip_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self._L = lib()
@@ -71,15 +74,22 @@ class Engine:
         if dev.type != "cuda":
             raise RuntimeError(f"plip_b200 runs on CUDA devices only, got {dev}")
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
-        blob, scale = pack_state_dict(state_dict)
+        fmt, _ = operand_format(operand_dtype)
+        self.operand_dtype = "fp16" if fmt == 1 else "bf16"
+        blob, scale = pack_state_dict(state_dict, self.operand_dtype)
         self.logit_scale_exp = float(scale)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             torch.cuda.init()
-            check(self._L.plip_create(blob.data_ptr(), blob.numel(), C.c_float(scale), self.device.index,
-                                      int(max_micro_batch), C.byref(h)), "plip_create")
+            check(self._L.plip_create_ex(blob.data_ptr(), blob.numel(), C.c_float(scale), self.device.index,
+                                         int(max_micro_batch), fmt, C.byref(h)), "plip_create_ex")
         self._h = h
         self.max_micro_batch = int(max_micro_batch)
+
+    def set_text_pooling(self, no_eos_argmax: bool) -> None:
+        """Captions without an eos token: pool position 0 (HF, ``eos_token_id == 49407``; default) or the first argmax
+        of the ids (legacy HF configs with ``eos_token_id == 2``, OpenAI clip).  See ``plip_set_text_pooling``."""
+        check(self._L.plip_set_text_pooling(self._h, int(bool(no_eos_argmax))), "plip_set_text_pooling")
 
     def close(self) -> None:
         if getattr(self, "_h", None):

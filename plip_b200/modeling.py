@@ -40,14 +40,15 @@ class PlipCLIPModel:
     """CUDA-engine-backed stand-in for ``CLIPModel`` (ViT-B/32 geometry only, as PLIP ships)."""
 
     def __init__(self, state_dict: Mapping[str, torch.Tensor], device: Union[int, str, torch.device, None] = None,
-                 max_micro_batch: int = 1024):
-        self.engine = Engine(state_dict, device=device, max_micro_batch=max_micro_batch)
+                 max_micro_batch: int = 1024, operand_dtype="bf16"):
+        self.engine = Engine(state_dict, device=device, max_micro_batch=max_micro_batch, operand_dtype=operand_dtype)
         self.device = self.engine.device
         self.training = False
 
     # ---- construction -------------------------------------------------------------------------
     @classmethod
-    def from_pretrained(cls, name_or_path: str, device=None, max_micro_batch: int = 1024, **hf_kwargs):
+    def from_pretrained(cls, name_or_path: str, device=None, max_micro_batch: int = 1024, operand_dtype="bf16",
+                        **hf_kwargs):
         """Read a HuggingFace CLIP checkpoint (e.g. ``vinid/plip`` or a local directory) on the host and pack
         it for the engine.  ``transformers`` is only the checkpoint *reader* here; its forward never runs.
         ``use_auth_token`` (reference ``plip.py:26``) is translated to ``token`` for transformers >= 5."""
@@ -58,15 +59,32 @@ class PlipCLIPModel:
             hf_kwargs.setdefault("token", tok)
         hf = CLIPModel.from_pretrained(name_or_path, **hf_kwargs)
         cfg = hf.config
-        if (cfg.vision_config.hidden_size, cfg.vision_config.patch_size, cfg.text_config.hidden_size,
-                cfg.projection_dim) != (768, 32, 512, 512):
-            raise ValueError("plip_b200 implements the CLIP ViT-B/32 geometry only (PLIP's architecture)")
-        return cls(hf.state_dict(), device=device, max_micro_batch=max_micro_batch)
+        v, t = cfg.vision_config, cfg.text_config
+        # every field the kernels hard-code (common.cuh model constants; TF:configuration_clip.py:47-64,97-109)
+        want = {"vision hidden_size": (v.hidden_size, 768), "vision patch_size": (v.patch_size, 32),
+                "vision image_size": (v.image_size, 224), "vision num_hidden_layers": (v.num_hidden_layers, 12),
+                "vision num_attention_heads": (v.num_attention_heads, 12), "vision intermediate_size": (v.intermediate_size, 3072),
+                "vision hidden_act": (v.hidden_act, "quick_gelu"), "vision layer_norm_eps": (float(v.layer_norm_eps), 1e-5),
+                "text hidden_size": (t.hidden_size, 512), "text num_hidden_layers": (t.num_hidden_layers, 12),
+                "text num_attention_heads": (t.num_attention_heads, 8), "text intermediate_size": (t.intermediate_size, 2048),
+                "text hidden_act": (t.hidden_act, "quick_gelu"), "text layer_norm_eps": (float(t.layer_norm_eps), 1e-5),
+                "text max_position_embeddings": (t.max_position_embeddings, 77), "text vocab_size": (t.vocab_size, 49408),
+                "projection_dim": (cfg.projection_dim, 512)}
+        bad = {k: got for k, (got, exp) in want.items() if got != exp}
+        if bad:
+            raise ValueError("plip_b200 implements the CLIP ViT-B/32 geometry only (PLIP's architecture); this "
+                             f"checkpoint differs in {bad}")
+        m = cls(hf.state_dict(), device=device, max_micro_batch=max_micro_batch, operand_dtype=operand_dtype)
+        # legacy configs (eos_token_id == 2) pool at argmax(input_ids) (TF:564-570); same row whenever an eos exists
+        m.engine.set_text_pooling(getattr(t, "eos_token_id", 49407) == 2)
+        return m
 
     @classmethod
-    def from_openai_state_dict(cls, state_dict, device=None, max_micro_batch: int = 1024):
+    def from_openai_state_dict(cls, state_dict, device=None, max_micro_batch: int = 1024, operand_dtype="bf16"):
         """``clip.load(arch)`` + ``load_state_dict(torch.load(path))`` (``embedders/factory.py:20-27``)."""
-        return cls(state_dict, device=device, max_micro_batch=max_micro_batch)
+        m = cls(state_dict, device=device, max_micro_batch=max_micro_batch, operand_dtype=operand_dtype)
+        m.engine.set_text_pooling(True)          # OpenAI clip: x[arange, text.argmax(-1)] (eot has the largest id)
+        return m
 
     # ---- nn.Module-ish no-ops the reference calls -------------------------------------------------
     def to(self, *args, **kwargs):

@@ -91,8 +91,22 @@ def tensor_table():
     return infos
 
 
-def pack_state_dict(state_dict: Mapping[str, torch.Tensor]) -> Tuple[torch.Tensor, float]:
-    """Return ``(blob, exp(logit_scale))``; ``blob`` is a contiguous CPU uint8 tensor."""
+OPERAND_DTYPES = {"bf16": (0, torch.bfloat16), "bfloat16": (0, torch.bfloat16),
+                  "fp16": (1, torch.float16), "float16": (1, torch.float16), "half": (1, torch.float16)}
+
+
+def operand_format(operand_dtype) -> Tuple[int, torch.dtype]:
+    """``"bf16"`` / ``"fp16"`` (or the torch dtype) -> ``(plip_operand_format, torch dtype)``."""
+    key = str(operand_dtype).replace("torch.", "")
+    if key not in OPERAND_DTYPES:
+        raise ValueError(f"operand_dtype must be 'bf16' or 'fp16', got {operand_dtype!r}")
+    return OPERAND_DTYPES[key]
+
+
+def pack_state_dict(state_dict: Mapping[str, torch.Tensor], operand_dtype="bf16") -> Tuple[torch.Tensor, float]:
+    """Return ``(blob, exp(logit_scale))``; ``blob`` is a contiguous CPU uint8 tensor.  GEMM weights are rounded
+    once to ``operand_dtype`` (the format the engine is created with: ``plip_create_ex``)."""
+    _, odt = operand_format(operand_dtype)
     sd = normalize_state_dict(state_dict)
     L = lib()
     blob = torch.zeros(int(L.plip_weights_blob_bytes()), dtype=torch.uint8)
@@ -119,10 +133,10 @@ def pack_state_dict(state_dict: Mapping[str, torch.Tensor]) -> Tuple[torch.Tenso
             gamma = sd[ln + ".weight"].detach().to(torch.float32)
             beta = sd[ln + ".bias"].detach().to(torch.float32)
             b = b + w @ beta
-            w = (w * gamma[None, :]).to(torch.bfloat16).to(torch.float32)
+            w = (w * gamma[None, :]).to(odt).to(torch.float32)
         folded[(base, "weight")] = w
         folded[(base, "bias")] = b
-        folded[(base, "colsum")] = w.to(torch.bfloat16).to(torch.float32).sum(dim=1)
+        folded[(base, "colsum")] = w.to(odt).to(torch.float32).sum(dim=1)
 
     for ti in tensor_table():
         name = ti.name.decode()
@@ -138,7 +152,7 @@ def pack_state_dict(state_dict: Mapping[str, torch.Tensor]) -> Tuple[torch.Tenso
         if t.numel() != ti.numel:
             raise ValueError(f"{name}: expected {ti.numel} elements ({ti.rows}x{ti.cols}), got {t.numel()}")
         if ti.dtype == 1:
-            raw = t.to(torch.bfloat16).contiguous().view(torch.uint8)
+            raw = t.to(odt).contiguous().view(torch.uint8)
         else:
             raw = t.contiguous().view(torch.uint8)
         blob[ti.offset: ti.offset + raw.numel()] = raw
