@@ -17,7 +17,11 @@ enum GemmEpilogue : int {
   EPI_LN_BIAS_BF16 = 5,       // layer_norm1 + q/k/v projection            (TF:371, 310-312)
   EPI_LN_BIAS_GELU_BF16 = 6,  // layer_norm2 + fc1 + QuickGELU             (TF:380, 348-349)
   EPI_NULL = 7,               // (diagnostic) accumulators are read from TMEM and dropped: main-loop-only rate
-  EPI_COUNT = 8
+  // Similarity head on the tensor cores (similarity.cu): out_f32[r,c] = acc * rowscale[r] * colscale[c].  The operands
+  // are fp16 hi/lo splits of power-of-two-scaled embeddings ([hi|lo|hi] x [hi|hi|lo], K = 3 x 512), the scales undo
+  // the power of two and carry logit_scale and the optional 1/|x| normalisation.   (TF:modeling_clip.py:923-930)
+  EPI_SIM_F32 = 8,
+  EPI_COUNT = 9
 };
 
 constexpr int kStatSlots = 8;  // per-row partial statistics slots (two per N tile of the producing GEMM: one per epilogue warp half)
@@ -28,7 +32,8 @@ struct GemmArgs {
   const __nv_bfloat16* W = nullptr;  // [N, K] row-major (nn.Linear weight layout), row stride ldw
   int ldw = 0;
   int M = 0, N = 0, K = 0;
-  const float* bias = nullptr;       // [N]
+  const float* bias = nullptr;       // [N]   (EPI_SIM_F32: the column scales)
+  const float* rowscale = nullptr;   // [M]   EPI_SIM_F32 only
   void* out = nullptr;               // bf16 or fp32 depending on epilogue; row stride ldo elements
   int ldo = 0;
   const float* pos = nullptr;        // EPI_PATCH_F32: vision position embedding [50, N]

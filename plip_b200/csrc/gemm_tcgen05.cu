@@ -61,6 +61,7 @@ struct GemmDev {
   int tma_store;  // bf16 epilogues: write the staged blocks with TMA bulk stores instead of read-back + STG
   int dbg;  // diagnostic (PLIP_GEMM_DBG): 1 = no global stores, 2 = no staging and no stores, 3 = no math either
   const float* bias;
+  const float* rowscale;
   void* out;
   int ldo;
   const float* pos;
@@ -260,6 +261,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
               st1[i] += s.x + s.y;
               st2[i] += q.x + q.y;
             }
+          } else if constexpr (EPI == EPI_SIM_F32) {
+            const float rs = __ldg(p.rowscale + grow);
+            const float4 cs = ld_shared_f4(bias_smem + (blk * 32 + rb_chunk * 4) * 4);
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldo + col) =
+                make_float4(v.x * rs * cs.x, v.y * rs * cs.y, v.z * rs * cs.z, v.w * rs * cs.w);
           } else if constexpr (EPI == EPI_PATCH_F32) {
             const int b = grow / kPatches;
             const int pp = grow - b * kPatches;
@@ -406,7 +412,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp < kEpiWarps) {
     // ===================== epilogue =====================
     constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
-    constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD);
+    constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD ||
+                               EPI == EPI_SIM_F32);  // the smem "bias" tile carries the column scales for EPI_SIM_F32
     const int q = warp & 3;          // the TMEM lane quarter this warp may access (warp % 4)
     const int half = warp >> 2;      // which interleaved half of the tile's column blocks it handles
     const int etid = threadIdx.x;
@@ -550,7 +557,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   static const int env_dbg = env_int("PLIP_GEMM_DBG", 0);
   p.dbg = env_dbg;
   p.tma_store = tma_store ? 1 : 0;
-  p.bias = g.bias; p.out = g.out; p.ldo = g.ldo; p.pos = g.pos;
+  p.bias = g.bias; p.rowscale = g.rowscale; p.out = g.out; p.ldo = g.ldo; p.pos = g.pos;
   p.colsum = g.colsum; p.stats_in = g.stats_in; p.n_partials = g.n_partials;
   p.xb_out = g.xb_out; p.stats_out = g.stats_out;
   if (g.n_tiles_used) *g.n_tiles_used = 2 * (g.N / BN);
@@ -575,6 +582,7 @@ int launch_epi_fmt(const GemmArgs& g, cudaStream_t stream) {
     case EPI_LN_BIAS_BF16: return launch_inst<CG, BN, EPI_LN_BIAS_BF16, F16>(g, stream);
     case EPI_LN_BIAS_GELU_BF16: return launch_inst<CG, BN, EPI_LN_BIAS_GELU_BF16, F16>(g, stream);
     case EPI_NULL: return launch_inst<CG, BN, EPI_NULL, F16>(g, stream);
+    case EPI_SIM_F32: return launch_inst<CG, BN, EPI_SIM_F32, F16>(g, stream);
     default: set_last_error("launch_gemm: bad epilogue %d", g.epi); return -2;
   }
 }
@@ -597,6 +605,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (g.epi == EPI_LN_BIAS_BF16 || g.epi == EPI_LN_BIAS_GELU_BF16)
     PLIP_REQUIRE(g.colsum && g.stats_in && g.bias && g.n_partials >= 1 && g.n_partials <= kStatSlots,
                  "launch_gemm: LayerNorm-folded epilogue needs colsum, stats and 1..%d partials", kStatSlots);
+  if (g.epi == EPI_SIM_F32)
+    PLIP_REQUIRE(g.bias && g.rowscale, "launch_gemm: the similarity epilogue needs row and column scales");
   if (g.xb_out || g.stats_out)
     PLIP_REQUIRE(g.epi == EPI_BIAS_RESID_F32 && g.xb_out && g.stats_out,
                  "launch_gemm: xb/stats outputs belong to the residual epilogue");

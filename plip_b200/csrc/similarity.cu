@@ -9,6 +9,9 @@
 // accumulated from the same operand tiles that feed the product, so each input is read once per tile.
 #include "kernels.cuh"
 
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace plip {
@@ -339,6 +342,125 @@ similarity_topk_tiled_kernel(const float* __restrict__ Q, int64_t n, const float
   }
 }
 
+
+// ---- similarity on the tensor cores ------------------------------------------------------------------------------
+// scale * norm(a) . norm(b)^T as ONE tcgen05 GEMM with fp32-class accuracy: every embedding row is scaled by a power
+// of two to max|x| in [32, 64) and split into fp16 hi + lo (22 significand bits, every fp16 x fp16 product exact in the
+// fp32 accumulator); with A' = [hi | lo | hi] and B' = [hi | hi | lo] (K = 3 x 512) the GEMM sums hi.hi + lo.hi + hi.lo
+// (the dropped lo.lo term is 2^-22 relative).  Row / column scale vectors undo the powers of two and carry logit_scale
+// and the optional 1/|x|; they are applied by the GEMM's EPI_SIM_F32 epilogue.  Error vs fp64: ~1e-6 relative, i.e.
+// |dlogits| ~1e-4 at scale 100 — the fp32 SIMT kernel above stays as the fallback for outputs whose leading dimension
+// cannot take the 128-column padding.  [125000 x 10000] (cfg5, one rank): 1.28 TFLOP of fp32 FMAs -> 3.9 TFLOP of MMAs.
+constexpr int kSplitK = 3 * kProj;
+
+__global__ void __launch_bounds__(256)
+split_embed_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int normalize, int role_b, float scale,
+                   __half* __restrict__ out, float* __restrict__ vec_scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_pad; r += nwarps) {
+    __half* o = out + r * kSplitK;
+    if (r >= n) {  // padding rows of the B operand: zeros, unit scale
+      for (int j = lane; j < kSplitK / 8; j += 32) reinterpret_cast<uint4*>(o)[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (lane == 0) vec_scale[r] = 0.f;
+      continue;
+    }
+    const float4* xr = reinterpret_cast<const float4*>(x + r * kProj);
+    float4 v[kProj / 128];
+    float ss = 0.f, mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < kProj / 128; ++j) {
+      v[j] = __ldg(xr + lane + 32 * j);
+      ss += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+      mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[j].x), fabsf(v[j].y))), fmaxf(fabsf(v[j].z), fabsf(v[j].w)));
+    }
+    ss = warp_sum(ss);
+    mx = warp_max(mx);
+    // power of two that brings max|x| into [32, 64): exact scaling, no fp16 subnormals in the lo parts that matter
+    int e = 0;
+    frexpf(mx, &e);                                   // mx = m * 2^e, m in [0.5, 1)
+    const float p2 = (mx > 0.f) ? exp2f((float)(6 - e)) : 1.0f;
+    const float undo = 1.0f / p2;                     // exact
+    if (lane == 0) vec_scale[r] = undo * (normalize ? rsqrtf(ss) : 1.0f) * scale;
+#pragma unroll
+    for (int j = 0; j < kProj / 128; ++j) {
+      const float f[4] = {v[j].x * p2, v[j].y * p2, v[j].z * p2, v[j].w * p2};
+      __half hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        hi[q] = __float2half_rn(f[q]);
+        lo[q] = __float2half_rn(f[q] - __half2float(hi[q]));
+      }
+      const uint2 uh = make_uint2(*reinterpret_cast<uint32_t*>(&hi[0]), *reinterpret_cast<uint32_t*>(&hi[2]));
+      const uint2 ul = make_uint2(*reinterpret_cast<uint32_t*>(&lo[0]), *reinterpret_cast<uint32_t*>(&lo[2]));
+      const int c = lane + 32 * j;                    // 4-element group inside the 512-wide block
+      reinterpret_cast<uint2*>(o)[c] = uh;                                  // block 0: hi
+      reinterpret_cast<uint2*>(o + kProj)[c] = role_b ? uh : ul;            // block 1: A lo / B hi
+      reinterpret_cast<uint2*>(o + 2 * kProj)[c] = role_b ? ul : uh;        // block 2: A hi / B lo
+    }
+  }
+}
+
+// grow-only per-device scratch for the split operands and the scale vectors (plip_similarity has no engine handle)
+struct SimScratch {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaEvent_t ev = nullptr;
+};
+SimScratch g_sim_pool[64];
+std::mutex g_sim_mu;
+
+constexpr int64_t kSimRowChunk = 131072;  // A rows split + multiplied per pass (403 MB of fp16 operand scratch)
+
+int launch_similarity_tc(const float* a, int64_t n, const float* b, int64_t m, float scale, bool norm_a, bool norm_b,
+                         float* out, int64_t ldo, cudaStream_t st) {
+  const int64_t m_pad = (m + 127) / 128 * 128;
+  const int64_t rows = n < kSimRowChunk ? n : kSimRowChunk;
+  const size_t bytes_b = (size_t)m_pad * kSplitK * 2, bytes_a = (size_t)rows * kSplitK * 2;
+  const size_t want = bytes_b + bytes_a + (size_t)(m_pad + rows) * 4 + 1024;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_sim_mu);
+  SimScratch& sc = g_sim_pool[dev & 63];
+  if (!sc.ev) PLIP_CUDA_CHECK(cudaEventCreateWithFlags(&sc.ev, cudaEventDisableTiming));
+  if (sc.bytes < want) {
+    if (sc.p) {
+      PLIP_CUDA_CHECK(cudaEventSynchronize(sc.ev));
+      PLIP_CUDA_CHECK(cudaFree(sc.p));
+      sc.p = nullptr; sc.bytes = 0;
+    }
+    PLIP_CUDA_CHECK(cudaMalloc(&sc.p, want));
+    sc.bytes = want;
+  }
+  PLIP_CUDA_CHECK(cudaStreamWaitEvent(st, sc.ev, 0));
+  uint8_t* base = static_cast<uint8_t*>(sc.p);
+  __half* bsplit = reinterpret_cast<__half*>(base);
+  __half* asplit = reinterpret_cast<__half*>(base + bytes_b);
+  float* cscale = reinterpret_cast<float*>(base + bytes_b + bytes_a);
+  float* rscale = cscale + m_pad;
+  auto grid_for_rows = [](int64_t r) { int64_t g = (r + 7) / 8; return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g)); };
+  PLIP_CUDA_CHECK(launch_kernel(split_embed_kernel, dim3(grid_for_rows(m_pad)), dim3(256), 0, st, 1, b, m, m_pad,
+                                norm_b ? 1 : 0, 1, 1.0f, bsplit, cscale));
+  ++g_launch_count;
+  for (int64_t i = 0; i < n; i += rows) {
+    const int64_t cnt = n - i < rows ? n - i : rows;
+    PLIP_CUDA_CHECK(launch_kernel(split_embed_kernel, dim3(grid_for_rows(cnt)), dim3(256), 0, st, 1, a + i * kProj, cnt, cnt,
+                                  norm_a ? 1 : 0, 0, scale, asplit, rscale));
+    ++g_launch_count;
+    GemmArgs g;
+    g.f16 = 1;
+    g.A = reinterpret_cast<const __nv_bfloat16*>(asplit); g.lda = kSplitK;
+    g.W = reinterpret_cast<const __nv_bfloat16*>(bsplit); g.ldw = kSplitK;
+    g.M = (int)cnt; g.N = (int)m_pad; g.K = kSplitK;
+    g.bias = cscale; g.rowscale = rscale;
+    g.out = out + i * ldo; g.ldo = (int)ldo; g.epi = EPI_SIM_F32;
+    if (int rc = launch_gemm(g, st)) return rc;
+  }
+  PLIP_CUDA_CHECK(cudaEventRecord(sc.ev, st));
+  return 0;
+}
+
 }  // namespace
 
 int launch_similarity(const float* a, int64_t n, const float* b, int64_t m, float scale, bool norm_a, bool norm_b,
@@ -347,6 +469,13 @@ int launch_similarity(const float* a, int64_t n, const float* b, int64_t m, floa
   PLIP_REQUIRE(ldo >= m, "similarity: ld_logits %lld < m %lld", (long long)ldo, (long long)m);
   PLIP_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(out) & 15) == 0, "similarity: operands must be 16-byte aligned");
+  // Tensor-core path for wide score matrices (>= 256 columns) whenever the output rows can take the 128-column
+  // padding of the GEMM tile (plip_b200's own callers allocate ld_logits that way).
+  static const int sim_simt = [] { const char* v = getenv("PLIP_SIM_SIMT"); return (v && v[0] == '1') ? 1 : 0; }();
+  const int64_t m_pad = (m + 127) / 128 * 128;
+  // (the choice depends on m only, so a row-sharded call computes bit-identical rows to the unsharded one)
+  if (!sim_simt && m >= 256 && ldo >= m_pad && ldo % 4 == 0 && ldo < 0x7fffffff)
+    return launch_similarity_tc(a, n, b, m, scale, norm_a, norm_b, out, ldo, st);
   const int64_t gy = (n + TM - 1) / TM, gx = (m + TN - 1) / TN;
   PLIP_REQUIRE(gy <= 65535, "similarity: n=%lld too large for one launch (chunk rows)", (long long)n);
   dim3 grid((unsigned)gx, (unsigned)gy);

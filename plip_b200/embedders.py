@@ -19,7 +19,7 @@ import torch
 
 from .modeling import PlipCLIPModel
 from .tokenizer import find_tokenizer
-from .preprocess import SIZE, chunks, decode_rgb, device_resizable, pack_rgb, to_uint8_tiles
+from .preprocess import decode_native_then_rgb, SIZE, chunks, decode_rgb, device_resizable, pack_rgb, to_uint8_tiles
 
 
 class AbstractEmbedder(ABC):
@@ -71,7 +71,7 @@ class CLIPEmbedder(AbstractEmbedder):
         for chunk in chunks(list(list_of_images), max(int(batch_size), 256)):
             # torchvision's CenterCrop rounding (transform.py:45-52), not CLIPImageProcessor's floor
             if eng is not None:
-                arrays = decode_rgb(chunk, int(num_workers))
+                arrays = decode_native_then_rgb(chunk, int(num_workers), crop="round")  # non-RGB modes: PIL, native mode
                 if all(a.shape == (SIZE, SIZE, 3) for a in arrays):
                     outs.append(eng.encode_images_host(np.stack(arrays, axis=0), normalize=True))
                 elif not all(device_resizable(a.shape[1], a.shape[0]) for a in arrays):  # too large: PIL
@@ -116,11 +116,39 @@ class EmbedderFactory:
         arch = os.environ.get("PC_CLIP_ARCH", "ViT-B/32")
         if arch != "ViT-B/32":
             raise ValueError(f"plip_b200 implements ViT-B/32 only (PC_CLIP_ARCH={arch!r})")
-        if name in ("plip", "clip"):
+        if name == "plip":      # clip.load(arch) + load_state_dict(torch.load(path))     (factory.py:20-27)
             sd = torch.load(path, map_location="cpu")
             if isinstance(sd, dict) and "state_dict" in sd:
                 sd = sd["state_dict"]
-            model = PlipCLIPModel(sd)
+            model = PlipCLIPModel.from_openai_state_dict(sd) if "visual.conv1.weight" in sd else PlipCLIPModel(sd)
+            model.eval()
+            return CLIPEmbedder(model, None, name, path)
+        if name == "clip":      # the PRETRAINED OpenAI weights; `path` is only a cache key there (factory.py:29-32)
+            model = PlipCLIPModel.from_openai_state_dict(self._openai_pretrained_state_dict(arch))
             model.eval()
             return CLIPEmbedder(model, None, name, path)
         raise ValueError(f"unsupported embedder {name!r} (plip / clip)")
+
+    @staticmethod
+    def _openai_pretrained_state_dict(arch: str):
+        """``clip.load(arch)``'s weights without running its model: through the ``clip`` package when it is
+        installed, else from its download cache (``~/.cache/clip/ViT-B-32.pt``, a TorchScript archive) or
+        ``$PLIP_B200_OPENAI_CLIP``.  Never falls back to ``args.backbone``: that is the PLIP checkpoint."""
+        try:
+            import clip                                   # noqa: PLC0415 - optional, as in the reference
+            model, _ = clip.load(arch, device="cpu")
+            return model.state_dict()
+        except ImportError:
+            pass
+        cands = [os.environ.get("PLIP_B200_OPENAI_CLIP"), os.path.expanduser("~/.cache/clip/ViT-B-32.pt")]
+        for c in cands:
+            if c and os.path.isfile(c):
+                try:
+                    return torch.jit.load(c, map_location="cpu").state_dict()
+                except RuntimeError:
+                    sd = torch.load(c, map_location="cpu")
+                    return sd["state_dict"] if isinstance(sd, dict) and "state_dict" in sd else sd
+        raise FileNotFoundError(
+            "embedder 'clip' needs OpenAI's pretrained ViT-B/32 weights: install the `clip` package, or put "
+            "ViT-B-32.pt into ~/.cache/clip/ (or point $PLIP_B200_OPENAI_CLIP at it).  args.backbone is NOT used for "
+            "this branch (reproducibility/embedders/factory.py:29-32 never loads it).")

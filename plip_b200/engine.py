@@ -174,7 +174,7 @@ class Engine:
         if a.shape[-1] != EMBED_DIM or b.shape[-1] != EMBED_DIM:
             raise ValueError("embeddings must have 512 columns")
         n, m = int(a.shape[0]), int(b.shape[0])
-        ld = (m + 3) // 4 * 4
+        ld = (m + 127) // 128 * 128          # the tensor-core path writes whole 128-column tiles
         out = torch.empty(n, ld, device=self.device, dtype=torch.float32)
         if n == 0 or m == 0:
             return out[:, :m]

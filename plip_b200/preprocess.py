@@ -117,6 +117,29 @@ def decode_rgb(images: Sequence[ImageLike], workers: int = 0) -> List[np.ndarray
     return [np.asarray(load_rgb(im)) for im in images]
 
 
+def decode_native_then_rgb(images: Sequence[ImageLike], workers: int = 0, crop: str = "round") -> List[np.ndarray]:
+    """Decode for the OpenAI-clip ``_transform`` order (``reproducibility/embedders/transform.py:45-52``: Resize ->
+    CenterCrop -> convert("RGB")): images that are already RGB come back as decoded arrays of any size (the caller
+    resizes them, on the device or with PIL — same result); images in ANY OTHER MODE (P / 1 / L / LA / RGBA / I;16 …)
+    are resized and cropped by PIL in their native mode first — Pillow picks NEAREST for palette / bilevel images and
+    resamples alpha-premultiplied for RGBA / LA, so converting first would change the tile — and come back as
+    finished 224x224 RGB tiles."""
+    def _one(im: ImageLike) -> np.ndarray:
+        if isinstance(im, str):
+            im = PIL.Image.open(im)
+        elif isinstance(im, np.ndarray):
+            im = PIL.Image.fromarray(im)
+        if im.mode != "RGB":
+            im = resize_center_crop(im, SIZE, crop).convert("RGB")
+        return np.asarray(im)
+
+    if workers > 1 and len(images) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            return list(ex.map(_one, images))
+    return [_one(im) for im in images]
+
+
 def to_uint8_tiles_device(images: Sequence[ImageLike], engine, crop: str = "floor", workers: int = 0):
     """Batch of images -> uint8 CUDA tensor ``[n,224,224,3]``: decode on the host, resize + crop on the device."""
     import torch

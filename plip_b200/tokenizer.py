@@ -1,4 +1,4 @@
-"""CLIP byte-level BPE tokenizer (captions -> ``[n,77]`` token ids) without the ``clip`` / ``tokenizers`` packages.
+r"""CLIP byte-level BPE tokenizer (captions -> ``[n,77]`` token ids) without the ``clip`` / ``tokenizers`` packages.
 
 The reference tokenises on the host in two flavours:
 
@@ -65,9 +65,42 @@ def base_vocab() -> List[str]:
     return v + [s + "</w>" for s in v]
 
 
+# ---- ftfy.fix_text, as OpenAI clip's basic_clean calls it (``embedders/plip.py:65`` -> clip.tokenize) ------------------
+# ``ftfy`` is a third-party package (un-pinned by the reference, absent from this image).  When it is importable it is
+# used; otherwise the deterministic character-level fixes of its DEFAULT configuration (ftfy 6.x ``TextFixerConfig``:
+# fix_latin_ligatures, fix_character_width, uncurl_quotes, fix_line_breaks, remove_terminal_escapes,
+# remove_control_chars, NFC) are restated here.  Its mojibake repair (fix_encoding, a heuristic search over
+# mis-decodings) is NOT restated: text that was decoded with the wrong codec tokenises differently without ftfy.
+_LIGATURES = {"\uFB00": "ff", "\uFB01": "fi", "\uFB02": "fl", "\uFB03": "ffi", "\uFB04": "ffl", "\uFB05": "\u017Ft", "\uFB06": "st",
+              "\u0132": "IJ", "\u0133": "ij", "\u0149": "\u02BCn", "\u01F1": "DZ", "\u01F2": "Dz", "\u01F3": "dz",
+              "\u01C4": "D\u017D", "\u01C5": "D\u017E", "\u01C6": "d\u017E", "\u01C7": "LJ", "\u01C8": "Lj", "\u01C9": "lj",
+              "\u01CA": "NJ", "\u01CB": "Nj", "\u01CC": "nj"}
+_FIX_TABLE = {ord(k): v for k, v in _LIGATURES.items()}
+_FIX_TABLE.update({c: "'" for c in [0x02BC] + list(range(0x2018, 0x201C))})        # uncurl_quotes: single
+_FIX_TABLE.update({c: '"' for c in range(0x201C, 0x2020)})                         # uncurl_quotes: double
+_FIX_TABLE.update({c: chr(c - 0xFEE0) for c in range(0xFF01, 0xFF5F)})             # fix_character_width: fullwidth ASCII
+_FIX_TABLE[0x3000] = " "                                                           # ideographic space
+_FIX_TABLE.update({0x2028: "\n", 0x2029: "\n", 0x0085: "\n"})                      # fix_line_breaks
+_FIX_TABLE.update({c: None for c in list(range(0x00, 0x09)) + [0x0B] + list(range(0x0E, 0x20)) + [0x7F, 0xFEFF]
+                   + list(range(0x206A, 0x2070)) + list(range(0xFFF9, 0xFFFD))})   # remove_control_chars
+_ANSI_RE = re.compile(r"\033\[((?:\d|;)*)([a-zA-Z])")                              # remove_terminal_escapes
+
+
+def fix_text(text: str) -> str:
+    """``ftfy.fix_text`` if the package is present, else its deterministic default fixes (see above)."""
+    try:
+        import ftfy                                  # noqa: PLC0415 - optional dependency of the reference
+        return ftfy.fix_text(text)
+    except ImportError:
+        pass
+    text = html.unescape(text)
+    text = _ANSI_RE.sub("", text.replace("\r\n", "\n").replace("\r", "\n"))
+    return unicodedata.normalize("NFC", text.translate(_FIX_TABLE))
+
+
 def _clean(text: str, openai: bool) -> str:
-    if openai:   # basic_clean + whitespace_clean + lower; of ftfy.fix_text (not installed) only its NFC step is kept
-        text = html.unescape(html.unescape(unicodedata.normalize("NFC", text))).strip()
+    if openai:   # clip.simple_tokenizer: basic_clean (ftfy.fix_text + 2x html.unescape) + whitespace_clean + lower
+        text = html.unescape(html.unescape(fix_text(text))).strip()
         return re.sub(r"\s+", " ", text).strip().lower()
     # transformers: normalizers.Sequence([NFC(), Replace(Regex(r"\s+"), " "), Lowercase()]).  `tokenizers` lowercases
     # character by character, i.e. without str.lower()'s context rule for a word-final capital sigma.

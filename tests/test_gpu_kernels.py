@@ -196,6 +196,31 @@ def test_attention(L, n_seq, S, heads, causal, use_mask):
     assert err.max().item() < 0.03 and err.mean().item() < 2e-3
 
 
+def test_similarity_tensor_core_path(L):
+    """Wide score matrices (>= 256 columns) run as one tcgen05 GEMM on fp16 hi/lo splits (similarity.cu): fp32-class
+    accuracy at PLIP's largest trained logit scale (100), with and without on-the-fly normalisation, ragged sizes."""
+    g = torch.Generator().manual_seed(5)
+    for n, m, na, nb, mag in ((1000, 777, True, True, 1.0), (130, 300, False, False, 1.0), (257, 1024, True, False, 37.0)):
+        a = (torch.randn(n, 512, generator=g) * mag).cuda()
+        b = torch.randn(m, 512, generator=g).cuda()
+        if not nb:
+            b = b / b.norm(dim=1, keepdim=True)
+        if not na:
+            a = a / a.norm(dim=1, keepdim=True)
+        ld = (m + 127) // 128 * 128
+        out = torch.full((n, ld), float("nan"), device="cuda")
+        _check(L.plip_similarity(a.data_ptr(), n, b.data_ptr(), m, 100.0, int(na), int(nb), out.data_ptr(), ld, _stream()), "sim")
+        torch.cuda.synchronize()
+        ad, bd = a.double(), b.double()
+        if na:
+            ad = ad / ad.norm(dim=1, keepdim=True)
+        if nb:
+            bd = bd / bd.norm(dim=1, keepdim=True)
+        ref = 100.0 * ad @ bd.t()
+        err = (out[:, :m].double() - ref).abs().max().item()
+        assert err < 2e-4, (n, m, err)                       # |dlogits| at scale 100 (north_star bar: 1e-3)
+
+
 def test_similarity_and_topk(L):
     dev = "cuda"
     a, b = torch.randn(300, 512, device=dev), torch.randn(70, 512, device=dev)

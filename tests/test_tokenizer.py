@@ -117,6 +117,23 @@ def test_openai_tokenize_convention(tok):
     assert np.array_equal((out == tok.eos_token_id).argmax(1)[plain], (hf_style == tok.eos_token_id).argmax(1)[plain])
 
 
+def test_openai_flavour_applies_ftfy_default_fixes(tok):
+    """clip.tokenize cleans captions with ftfy.fix_text (embedders/plip.py:65): curly quotes, ligatures, fullwidth
+    characters and control characters must tokenise like their plain spellings (Twitter-sourced OpenPath
+    captions are full of them).  Vectors: ftfy 6.x default configuration (uncurl_quotes, fix_latin_ligatures,
+    fix_character_width, remove_control_chars, fix_line_breaks)."""
+    from plip_b200.tokenizer import fix_text
+    pairs = [("It\u2019s a \u201cfine\u201d tumor", "It's a \"fine\" tumor"),
+             ("\ufb01brosis and in\ufb02ammation", "fibrosis and inflammation"),
+             ("\uff28\uff06\uff25 stain\u3000image", "H&E stain image"),
+             ("mitotic\x07 figure\ufeff", "mitotic figure"),
+             ("line one\u2028line two", "line one\nline two")]
+    for raw, plain in pairs:
+        assert fix_text(raw) == plain, (raw, fix_text(raw))
+        assert np.array_equal(tok.tokenize([raw])[0], tok.tokenize([plain])[0])
+    assert fix_text("Ki-67 &amp; HER2") == "Ki-67 & HER2"                   # unescape_html
+
+
 def test_decode_round_trip(tok):
     for t in ["tumor stroma", "café naïve"]:
         assert tok.decode(tok.encode(t)).strip() == t

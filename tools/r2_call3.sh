@@ -4,6 +4,10 @@ set -x
 mkdir -p gpurun_out
 cd $GRAFT_REPO_ROOT
 nvidia-smi --query-gpu=index,name,clocks.sm,power.draw --format=csv > gpurun_out/r2c_smi.txt
+# the tensor-core similarity path is new: validate it on one GPU first, fall back to the fp32 SIMT kernel if it fails
+CUDA_VISIBLE_DEVICES=0 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -m gpu -x -q -k "similarity or clip_forward or evaluation" > gpurun_out/r2c_pytest_sim.log 2>&1
+if [ $? -ne 0 ]; then export PLIP_SIM_SIMT=1; echo "TC similarity FAILED: using SIMT" >> gpurun_out/r2c_rc.txt; fi
+tail -3 gpurun_out/r2c_pytest_sim.log
 ( time python -m pytest tests/test_gpu_multi.py -m gpu -x -q ) > gpurun_out/r2c_pytest_multi.log 2>&1
 tail -3 gpurun_out/r2c_pytest_multi.log
 run() {  # N configs steps
