@@ -14,9 +14,12 @@
 // on this path.
 #include "kernels.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace plip {
@@ -157,6 +160,18 @@ struct plip_engine {
   size_t d_out_bytes = 0;
   void* d_aux = nullptr;  // ids + mask for the text host path
   size_t d_aux_bytes = 0;
+  // small-batch path: the ~67 launches of a tower are replayed as ONE CUDA graph per (tower, n, input format ...) on
+  // engine-owned staging buffers (inputs are copied in, the [n,512] result copied out), which removes the host-side
+  // launch cost that dominates when a forward is only a few hundred microseconds of GPU work (reference default:
+  // batch_size = 8, plip.py:95-97).  PLIP_GRAPH_MAX (default 128, 0 = off) bounds n.
+  int graph_max_n = 128;
+  cudaStream_t s_cap = nullptr;
+  void* g_in = nullptr;        // staged pixels / ids
+  size_t g_in_bytes = 0;
+  void* g_mask = nullptr;
+  size_t g_mask_bytes = 0;
+  float* g_out = nullptr;      // [graph_max_n, 512]
+  std::map<std::tuple<int, int, int, int, int, int, int>, cudaGraphExec_t> graphs;
   // in-step kernel timing (plip_profile_*): a CUDA event pair around every launch of a forward pass, recorded on
   // the launch stream, so bench.py can report each kernel's average duration INSIDE the step it belongs to
   bool prof_on = false;
@@ -507,6 +522,33 @@ bool is_pinned(const void* p) {
 
 }  // namespace
 
+namespace {
+
+// Capture `body` (stream-ordered launches on e->s_cap, nothing executes) into an executable graph.
+template <typename F>
+int capture_graph(plip_engine* e, F&& body, cudaGraphExec_t* out) {
+  if (!e->s_cap) PLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&e->s_cap, cudaStreamNonBlocking));
+  PLIP_CUDA_CHECK(cudaStreamBeginCapture(e->s_cap, cudaStreamCaptureModeThreadLocal));
+  const int rc = body(e->s_cap);
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(e->s_cap, &g);
+  if (rc != 0) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  PLIP_CUDA_CHECK(ce);
+  const cudaError_t ci = cudaGraphInstantiate(out, g, 0);
+  cudaGraphDestroy(g);
+  PLIP_CUDA_CHECK(ci);
+  return 0;
+}
+
+bool graph_eligible(const plip_engine* e, int64_t n) {
+  return e->graph_max_n > 0 && n <= e->graph_max_n && n <= e->max_mb && !e->prof_on;
+}
+
+}  // namespace
+
 // ================================================================================================
 // C ABI
 // ================================================================================================
@@ -564,6 +606,7 @@ PLIP_API int plip_create_ex(const void* host_blob, uint64_t nbytes, float logit_
   e->device = device;
   e->max_mb = max_micro_batch;
   e->f16 = operand_format == PLIP_OPERAND_FP16 ? 1 : 0;
+  if (const char* gm = getenv("PLIP_GRAPH_MAX")) e->graph_max_n = atoi(gm) < 0 ? 0 : (atoi(gm) > 1024 ? 1024 : atoi(gm));
   e->logit_scale_exp = logit_scale_exp;
   const WsLayout w = ws_layout(max_micro_batch);
   uint8_t* ws = nullptr;
@@ -615,6 +658,11 @@ PLIP_API int plip_destroy(plip_engine_t* e) {
   if (e->d_out) cudaFree(e->d_out);
   if (e->d_aux) cudaFree(e->d_aux);
   if (e->ev_last) cudaEventDestroy(e->ev_last);
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  if (e->g_in) cudaFree(e->g_in);
+  if (e->g_mask) cudaFree(e->g_mask);
+  if (e->g_out) cudaFree(e->g_out);
+  if (e->s_cap) cudaStreamDestroy(e->s_cap);
   for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
   if (e->s_compute) cudaStreamDestroy(e->s_compute);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
@@ -677,6 +725,26 @@ PLIP_API int plip_encode_images(plip_engine_t* e, const void* pixels_dev, int pi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PLIP_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_last, 0));  // calls on different streams share one workspace
   const size_t pb = pixel_bytes(pixel_format);
+  if (graph_eligible(e, n)) {
+    const auto key = std::make_tuple(0, (int)n, pixel_format, normalize ? 1 : 0, 0, 0, 0);
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+      // first call of this shape: run it eagerly (this also configures every kernel), then record the graph
+      if (int rc = grow_dev(&e->g_in, &e->g_in_bytes, (size_t)e->graph_max_n * pixel_bytes(PLIP_PIX_F32_NCHW))) return rc;
+      if (!e->g_out) PLIP_CUDA_CHECK(cudaMalloc(&e->g_out, (size_t)e->graph_max_n * kProj * 4));
+      if (int rc = vision_forward(e, pixels_dev, pixel_format, n, out_dev, normalize, st)) return rc;
+      cudaGraphExec_t ge = nullptr;
+      if (int rc = capture_graph(e, [&](cudaStream_t cs) { return vision_forward(e, e->g_in, pixel_format, n, e->g_out, normalize, cs); }, &ge)) return rc;
+      e->graphs.emplace(key, ge);
+    } else {
+      PLIP_CUDA_CHECK(cudaMemcpyAsync(e->g_in, pixels_dev, (size_t)n * pb, cudaMemcpyDeviceToDevice, st));
+      PLIP_CUDA_CHECK(cudaGraphLaunch(it->second, st));
+      PLIP_CUDA_CHECK(cudaMemcpyAsync(out_dev, e->g_out, (size_t)n * kProj * 4, cudaMemcpyDeviceToDevice, st));
+      g_launch_count += 67;
+    }
+    PLIP_CUDA_CHECK(cudaEventRecord(e->ev_last, st));
+    return 0;
+  }
   for (int64_t i = 0; i < n; i += e->max_mb) {
     const int64_t mb = (n - i < e->max_mb) ? (n - i) : e->max_mb;
     if (int rc = vision_forward(e, static_cast<const uint8_t*>(pixels_dev) + i * pb, pixel_format, mb,
@@ -706,6 +774,31 @@ PLIP_API int plip_encode_text_prefix(plip_engine_t* e, const void* ids_dev, int 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PLIP_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_last, 0));
   const size_t isz = ids_dtype == PLIP_IDS_I64 ? 8 : 4;
+  if (graph_eligible(e, n)) {
+    const auto key = std::make_tuple(1, (int)n, ids_dtype, normalize ? 1 : 0, seq_len, prefix_len, attention_mask_dev ? 1 : 0);
+    const size_t ib = (size_t)n * seq_len * isz;
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+      if (int rc = grow_dev(&e->g_in, &e->g_in_bytes, (size_t)e->graph_max_n * pixel_bytes(PLIP_PIX_F32_NCHW))) return rc;
+      if (int rc = grow_dev(&e->g_mask, &e->g_mask_bytes, (size_t)e->graph_max_n * kTxtSeq * 8)) return rc;
+      if (!e->g_out) PLIP_CUDA_CHECK(cudaMalloc(&e->g_out, (size_t)e->graph_max_n * kProj * 4));
+      if (int rc = text_forward(e, ids_dev, ids_dtype, attention_mask_dev, n, prefix_len, seq_len, out_dev, normalize, st)) return rc;
+      cudaGraphExec_t ge = nullptr;
+      if (int rc = capture_graph(e, [&](cudaStream_t cs) {
+            return text_forward(e, e->g_in, ids_dtype, attention_mask_dev ? e->g_mask : nullptr, n, prefix_len, seq_len,
+                                e->g_out, normalize, cs);
+          }, &ge)) return rc;
+      e->graphs.emplace(key, ge);
+    } else {
+      PLIP_CUDA_CHECK(cudaMemcpyAsync(e->g_in, ids_dev, ib, cudaMemcpyDeviceToDevice, st));
+      if (attention_mask_dev) PLIP_CUDA_CHECK(cudaMemcpyAsync(e->g_mask, attention_mask_dev, ib, cudaMemcpyDeviceToDevice, st));
+      PLIP_CUDA_CHECK(cudaGraphLaunch(it->second, st));
+      PLIP_CUDA_CHECK(cudaMemcpyAsync(out_dev, e->g_out, (size_t)n * kProj * 4, cudaMemcpyDeviceToDevice, st));
+      g_launch_count += 66;
+    }
+    PLIP_CUDA_CHECK(cudaEventRecord(e->ev_last, st));
+    return 0;
+  }
   for (int64_t i = 0; i < n; i += e->max_mb) {
     const int64_t mb = (n - i < e->max_mb) ? (n - i) : e->max_mb;
     const uint8_t* ids = static_cast<const uint8_t*>(ids_dev) + i * seq_len * isz;

@@ -36,7 +36,6 @@ constexpr int kThreads = 384;      // 8 epilogue warps (0-7) + 4 control warps (
 constexpr int kWarpTma = 8, kWarpMma = 9, kWarpTmem = 10;  // highest warp ids: the SM sub-partition arbiter
                                                            // favours them over the instruction-heavy epilogue warps
 constexpr int kEpiWarps = 8;       // two per TMEM lane quarter, splitting the tile's column blocks
-constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr uint32_t A_STAGE = BM * BK * 2;
 
 template <int CG, int BN, int EPI = EPI_LN_BIAS_BF16>
@@ -45,8 +44,9 @@ struct Cfg {
   static constexpr uint32_t B_STAGE = LOAD_N * BK * 2;
   static constexpr uint32_t STAGE = A_STAGE + B_STAGE;
   static constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
-  // per-warp staging blocks + double-buffered bias tile (+ double-buffered colsum tile for the LN fold)
-  static constexpr uint32_t EPI_BYTES = kEpiWarps * 32 * 128 + (LN_FOLD ? 4 : 2) * BN * 4;
+  // per-warp staging blocks + per-warp bias slice (+ colsum slice for the LN fold): a warp owns BN / 2 columns
+  static constexpr uint32_t VEC_BYTES = (LN_FOLD ? 2 : 1) * (BN / 2) * 4;  // per warp
+  static constexpr uint32_t EPI_BYTES = kEpiWarps * 32 * 128 + kEpiWarps * VEC_BYTES;
   static constexpr uint32_t BAR_BYTES = 256;
   // The dynamic smem window starts 1024-aligned (checked at kernel entry), so no alignment slack is
   // reserved: that is what lets the residual epilogues run a 6-deep 32 KB operand ring.
@@ -94,8 +94,8 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 }
 
 // acc (+ bias from the smem bias tile) for 32 consecutive columns of this thread's row, as 16 float2 (packed fp32 math).
-// LN_FOLD: rstd * acc + (bias' - (rstd * mean) * colsum)  ==  rstd * (acc - mean * colsum) + bias'; the colsum tile is
-// stored BN floats after the bias tile pair.  `nrm` = -rstd * mean.
+// LN_FOLD: rstd * acc + (bias' - (rstd * mean) * colsum)  ==  rstd * (acc - mean * colsum) + bias'; the warp's colsum
+// slice is stored BN / 2 floats after its bias slice.  `nrm` = -rstd * mean.
 template <bool HAS_BIAS, bool LN_FOLD, int BN>
 __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, float nrm, float rstd,
                                            float2 (&f)[16]) {
@@ -110,7 +110,7 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, f
     const float2 a0 = make_float2(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]));
     const float2 a1 = make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
     if constexpr (LN_FOLD) {
-      const float4 cs = ld_shared_f4(bias_smem + 2 * BN * 4 + 16 * i);
+      const float4 cs = ld_shared_f4(bias_smem + (BN / 2) * 4 + 16 * i);
       f[2 * i + 0] = __ffma2_rn(rstd2, a0, __ffma2_rn(nrm2, make_float2(cs.x, cs.y), make_float2(b.x, b.y)));
       f[2 * i + 1] = __ffma2_rn(rstd2, a1, __ffma2_rn(nrm2, make_float2(cs.z, cs.w), make_float2(b.z, b.w)));
     } else if constexpr (HAS_BIAS) {
@@ -155,21 +155,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
   if constexpr (OUT_BF16) {
 #pragma unroll 1
     for (int blk = half; blk < BN / 64; blk += 2) {
-      // 64 columns -> 128 B of bf16 per row
-      if (p.tma_store) {  // the previous bulk store must have finished reading this staging block
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-      }
+      // 64 columns -> 128 B of bf16 per row.  The math runs BEFORE the wait for the previous bulk store of this
+      // warp's staging block, so the store's smem read (and the TMEM load) overlap instead of serialising.
+      uint32_t pk[32];
+      bool skip = false;
 #pragma unroll
       for (int half2 = 0; half2 < 2; ++half2) {
         float2 f[16];
-        load_acc32<HAS_BIAS, LN_FOLD, BN>(tmem_row_base + blk * 64 + half2 * 32, bias_smem + (blk * 64 + half2 * 32) * 4,
+        load_acc32<HAS_BIAS, LN_FOLD, BN>(tmem_row_base + blk * 64 + half2 * 32, bias_smem + ((blk >> 1) * 64 + half2 * 32) * 4,
                                           mean, rstd, f);
         if (p.dbg >= 2) {
           float a = 0.f;
 #pragma unroll
           for (int i = 0; i < 16; ++i) a += f[i].x + f[i].y;
           if (a == 1.2345e30f) reinterpret_cast<float*>(p.out)[0] = a;
+          skip = true;
           continue;
         }
         if constexpr (GELU) {
@@ -177,13 +177,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
           for (int i = 0; i < 16; ++i) f[i] = quick_gelu2(f[i]);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int chunk = half2 * 4 + c;
-          st_shared_v4(my_row + ((chunk ^ sw) << 4), pack_op2<F16>(f[4 * c + 0].x, f[4 * c + 0].y),
-                       pack_op2<F16>(f[4 * c + 1].x, f[4 * c + 1].y), pack_op2<F16>(f[4 * c + 2].x, f[4 * c + 2].y),
-                       pack_op2<F16>(f[4 * c + 3].x, f[4 * c + 3].y));
-        }
+        for (int i = 0; i < 16; ++i) pk[half2 * 16 + i] = pack_op2<F16>(f[i].x, f[i].y);
       }
+      if (skip) continue;
+      if (p.tma_store) {  // the previous bulk store must have finished reading this staging block
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int chunk = 0; chunk < 8; ++chunk)
+        st_shared_v4(my_row + ((chunk ^ sw) << 4), pk[4 * chunk + 0], pk[4 * chunk + 1], pk[4 * chunk + 2], pk[4 * chunk + 3]);
       if (p.tma_store) {
         // the staging block is laid out exactly as a SWIZZLE_128B [32 rows x 64 bf16] TMA box
         fence_proxy_async_smem();
@@ -232,7 +235,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
       }
       {
         float2 f[16];
-        load_acc32<HAS_BIAS, false, BN>(tmem_row_base + blk * 32, bias_smem + blk * 32 * 4, 0.f, 1.f, f);
+        load_acc32<HAS_BIAS, false, BN>(tmem_row_base + blk * 32, bias_smem + (blk >> 1) * 32 * 4, 0.f, 1.f, f);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           st_shared_v4(my_row + ((c ^ sw) << 4), __float_as_uint(f[2 * c + 0].x), __float_as_uint(f[2 * c + 0].y),
@@ -263,7 +266,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
             }
           } else if constexpr (EPI == EPI_SIM_F32) {
             const float rs = __ldg(p.rowscale + grow);
-            const float4 cs = ld_shared_f4(bias_smem + (blk * 32 + rb_chunk * 4) * 4);
+            const float4 cs = ld_shared_f4(bias_smem + ((blk >> 1) * 32 + rb_chunk * 4) * 4);
             *reinterpret_cast<float4*>(out + static_cast<size_t>(grow) * p.ldo + col) =
                 make_float4(v.x * rs * cs.x, v.y * rs * cs.y, v.z * rs * cs.z, v.w * rs * cs.w);
           } else if constexpr (EPI == EPI_PATCH_F32) {
@@ -312,7 +315,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __trap();
   }
   const uint32_t epi_base = smem_base + STAGES * C::STAGE;   // 1024-aligned: 4 x 4 KB staging blocks
-  const uint32_t bias_base = epi_base + kEpiWarps * kEpiStageBytes;  // 2 x BN bias + 2 x BN colsum floats
+  const uint32_t bias_base = epi_base + kEpiWarps * kEpiStageBytes;  // per warp: BN / 2 bias (+ BN / 2 colsum) floats
   const uint32_t bar_base = smem_base + STAGES * C::STAGE + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -416,22 +419,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                EPI == EPI_SIM_F32);  // the smem "bias" tile carries the column scales for EPI_SIM_F32
     const int q = warp & 3;          // the TMEM lane quarter this warp may access (warp % 4)
     const int half = warp >> 2;      // which interleaved half of the tile's column blocks it handles
-    const int etid = threadIdx.x;
     int a = 0;
     uint32_t aph = 0;
     for (int t = tile0; t < num_tiles; t += tile_step) {
       const int m_blk = t / num_n_blk, n_blk = t - m_blk * num_n_blk;
       if constexpr (HAS_BIAS) {
-        // bias tile for this accumulator stage (its previous readers are two tiles behind us)
-        float* bs = reinterpret_cast<float*>(smem_raw + (bias_base - smem_raw_u32)) + a * BN;
-        for (int i = etid; i < BN; i += kEpiThreads) {
-          bs[i] = __ldg(p.bias + n_blk * BN + i);
+        // this warp's slice of the bias (and colsum) vector: the BN / 2 columns it will touch, in its own order
+        // (column blocks half, half + 2, ... of W columns).  Private to the warp: __syncwarp instead of a 256-thread
+        // barrier per tile (ncu r2b: "barrier" was the second stall reason of every epilogue).
+        constexpr bool kOut16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || LN_FOLD);
+        constexpr int W = kOut16 ? 64 : 32;
+        float* bs = reinterpret_cast<float*>(smem_raw + (bias_base - smem_raw_u32) + warp * C::VEC_BYTES);
+        __syncwarp();
+        for (int i = lane; i < BN / 2; i += 32) {
+          const int col = n_blk * BN + (half + 2 * (i / W)) * W + (i % W);
+          bs[i] = __ldg(p.bias + col);
+          if constexpr (LN_FOLD) bs[BN / 2 + i] = __ldg(p.colsum + col);
         }
-        if constexpr (LN_FOLD) {
-          float* cs = reinterpret_cast<float*>(smem_raw + (bias_base - smem_raw_u32)) + 2 * BN + a * BN;
-          for (int i = etid; i < BN; i += kEpiThreads) cs[i] = __ldg(p.colsum + n_blk * BN + i);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        __syncwarp();
       }
       const int row_base = m_blk * BM * CG + cta_rank * BM + q * 32;
       if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -475,7 +480,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      epilogue_tile<BN, EPI, F16>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + a * BN * 4, row_base,
+      epilogue_tile<BN, EPI, F16>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + warp * C::VEC_BYTES, row_base,
                              n_blk * BN, n_blk, half, lane, ln_mean, ln_rstd);
       tc_fence_before();
       __syncwarp();

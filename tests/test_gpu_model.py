@@ -156,6 +156,29 @@ def test_microbatching_host_path_and_determinism(engine):
     assert engine.encode_images(torch.zeros(0, 3, 224, 224)).shape == (0, 512)
 
 
+def test_small_batch_graph_replay_is_bit_identical(engine, state_dict):
+    """n <= 128: the first call of a shape runs the launches eagerly and records them as a CUDA graph, later calls
+    replay the graph on staged inputs (engine.cu).  Replays must reproduce the eager result bit for bit, for both
+    towers, with and without a mask, and must not leak one call's inputs into the next."""
+    px = synth.pixel_values(8, seed=51).cuda()
+    px2 = synth.pixel_values(8, seed=52).cuda()
+    ids, mask = synth.token_ids(8, seed=53)
+    ids2, mask2 = synth.token_ids(8, seed=54)
+    e1 = engine.encode_images(px).clone()                      # eager + capture
+    o2 = engine.encode_images(px2).clone()                     # replay, other input
+    e1b = engine.encode_images(px).clone()                     # replay, first input again
+    assert torch.equal(e1, e1b) and not torch.equal(e1, o2)
+    assert (1 - O.cosine(o2.cpu(), O.get_image_features(state_dict, px2.cpu()))).max().item() < COS_TOL
+    t1 = engine.encode_text(ids.cuda(), mask.cuda()).clone()
+    t2 = engine.encode_text(ids2.cuda(), mask2.cuda()).clone()
+    t1b = engine.encode_text(ids.cuda(), mask.cuda()).clone()
+    assert torch.equal(t1, t1b) and not torch.equal(t1, t2)
+    assert (1 - O.cosine(t2.cpu(), O.get_text_features(state_dict, ids2, mask2))).max().item() < COS_TOL
+    n1 = engine.encode_images(px, normalize=True)              # a different graph key (normalize)
+    assert torch.allclose(n1, e1 / e1.norm(dim=1, keepdim=True), atol=1e-6)
+    assert (1 - O.cosine(engine.encode_images(px[:3]).cpu(), e1[:3].cpu())).max().item() < 1e-6   # another n / graph
+
+
 def test_calls_on_different_streams_are_serialised(engine):
     """One handle = one workspace: back-to-back calls on different streams (and the host path right after a
     device call) must not corrupt each other."""
