@@ -481,7 +481,8 @@ def run_ours(args):
     from plip_b200 import distributed as D
     from plip_b200._lib import lib
     from plip_b200.modeling import PlipCLIPModel
-    model = PlipCLIPModel(sd, device=dev, max_micro_batch=PAIRS, operand_dtype=args.operands)
+    # PLIP_BENCH_MB: experiment knob — engine micro-batch below the 1024-pair step (activations closer to L2 size)
+    model = PlipCLIPModel(sd, device=dev, max_micro_batch=int(os.environ.get("PLIP_BENCH_MB", PAIRS)), operand_dtype=args.operands)
     ctx = {"args": args, "rank": rank, "ws": ws, "dev": dev, "peaks": peaks, "cpu": cpu, "sd": sd, "model": model,
            "eng": model.engine, "L": lib(), "sh": D.ShardedCLIP.from_engine(model.engine), "timer": Timer(dev, ws)}
     # several comma-separated configs share one process (one weight upload): one JSON line each — the driver's

@@ -461,6 +461,109 @@ int launch_similarity_tc(const float* a, int64_t n, const float* b, int64_t m, f
   return 0;
 }
 
+
+// ---- top-k on the tensor cores: score chunks from the split-fp16 GEMM, folded row by row ---------------------------
+// For big retrieval problems (cfg5: 10,000 queries x 125,000 gallery rows per rank) the fused fp32 SIMT kernel above
+// spends its time on FMAs (1.28 TFLOP -> ~88 ms).  Here the scores of all queries against a CHUNK of the space come
+// from launch_similarity_tc (0.5 ms per 16 k columns) into a scratch block, and one warp per query folds its row
+// into the query's running sorted top-k list (global memory, k <= 64): every lane tests 4 scores per iteration against
+// the current k-th best, survivors are inserted with the same warp-cooperative topk_insert — ~k ln(m / k) insertions
+// per row in total, so the pass is a streaming read of the chunk.  Ordering: score, then lower index (deterministic).
+constexpr int kMergeWarps = 8;
+
+__global__ void __launch_bounds__(kMergeWarps * 32)
+rowwise_topk_merge_kernel(const float* __restrict__ S, int64_t n, int64_t cols, int64_t ld, int64_t col0, int k,
+                          int first, int32_t* __restrict__ idx, float* __restrict__ val) {
+  __shared__ float lv[kMergeWarps][kTopkMax];
+  __shared__ int li[kMergeWarps][kTopkMax];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kMergeWarps + warp;
+  if (row >= n) return;
+  TopkLists L;
+  L.v = &lv[0][0];
+  L.i = &li[0][0];
+  for (int j = lane; j < kTopkMax; j += 32) {
+    const bool have = !first && j < k;
+    const int id = have ? idx[row * k + j] : -1;
+    lv[warp][j] = (have && id >= 0) ? val[row * k + j] : -INFINITY;
+    li[warp][j] = (have && id >= 0) ? id : 0x7fffffff;
+  }
+  __syncwarp();
+  const float* sr = S + row * ld;
+  for (int64_t c0 = 0; c0 < cols; c0 += 128) {
+    const int64_t c = c0 + lane * 4;
+    float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (c + 3 < cols) v = __ldg(reinterpret_cast<const float4*>(sr + c));
+    else {
+      if (c < cols) v.x = sr[c];
+      if (c + 1 < cols) v.y = sr[c + 1];
+      if (c + 2 < cols) v.z = sr[c + 2];
+    }
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float s = vv[q];
+      const int id = (int)(col0 + c + q);
+      const float thr = lv[warp][k - 1];
+      const int thr_i = li[warp][k - 1];
+      unsigned pass = __ballot_sync(0xffffffffu, s > -INFINITY && better(s, id, thr, thr_i));
+      while (pass) {
+        const int b = __ffs(pass) - 1;
+        pass &= pass - 1;
+        topk_insert(L, warp, k, __shfl_sync(0xffffffffu, s, b), __shfl_sync(0xffffffffu, id, b), lane);
+      }
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < k; j += 32) {
+    const int id = li[warp][j];
+    idx[row * k + j] = id == 0x7fffffff ? -1 : id;
+    val[row * k + j] = lv[warp][j];
+  }
+}
+
+SimScratch g_topk_tc_pool[64];
+
+int launch_similarity_topk_tc(const float* q, int64_t n, const float* s, int64_t m, float scale, bool norm_q,
+                              bool norm_s, int k, int32_t* idx, float* val, cudaStream_t st) {
+  // chunk of the space: <= 256 MB of fp32 scores for all n queries, a multiple of 256 columns
+  int64_t gc = ((int64_t)256 << 20) / (4 * n) / 256 * 256;
+  if (gc < 256) gc = 256;
+  if (gc > 32768) gc = 32768;
+  if (gc > (m + 255) / 256 * 256) gc = (m + 255) / 256 * 256;
+  const size_t score_bytes = (size_t)n * gc * 4, val_bytes = val ? 0 : (size_t)n * k * 4;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SimScratch& sc = g_topk_tc_pool[dev & 63];
+  {
+    std::lock_guard<std::mutex> lk(g_sim_mu);
+    if (!sc.ev) PLIP_CUDA_CHECK(cudaEventCreateWithFlags(&sc.ev, cudaEventDisableTiming));
+    if (sc.bytes < score_bytes + val_bytes + 256) {
+      if (sc.p) {
+        PLIP_CUDA_CHECK(cudaEventSynchronize(sc.ev));
+        PLIP_CUDA_CHECK(cudaFree(sc.p));
+        sc.p = nullptr; sc.bytes = 0;
+      }
+      PLIP_CUDA_CHECK(cudaMalloc(&sc.p, score_bytes + val_bytes + 256));
+      sc.bytes = score_bytes + val_bytes + 256;
+    }
+    PLIP_CUDA_CHECK(cudaStreamWaitEvent(st, sc.ev, 0));
+  }
+  float* scores = static_cast<float*>(sc.p);
+  float* vals = val ? val : reinterpret_cast<float*>(static_cast<uint8_t*>(sc.p) + score_bytes);
+  const unsigned grid = (unsigned)((n + kMergeWarps - 1) / kMergeWarps);
+  for (int64_t c0 = 0; c0 < m; c0 += gc) {
+    const int64_t cols = m - c0 < gc ? m - c0 : gc;
+    if (int rc = launch_similarity_tc(q, n, s + c0 * kProj, cols, scale, norm_q, norm_s, scores, gc, st)) return rc;
+    PLIP_CUDA_CHECK(launch_kernel(rowwise_topk_merge_kernel, dim3(grid), dim3(kMergeWarps * 32), 0, st, 1, scores, n, cols,
+                                  gc, c0, k, c0 == 0 ? 1 : 0, idx, vals));
+    ++g_launch_count;
+  }
+  std::lock_guard<std::mutex> lk(g_sim_mu);
+  PLIP_CUDA_CHECK(cudaEventRecord(sc.ev, st));
+  return 0;
+}
+
 }  // namespace
 
 int launch_similarity(const float* a, int64_t n, const float* b, int64_t m, float scale, bool norm_a, bool norm_b,
@@ -490,6 +593,9 @@ int launch_similarity_topk(const float* q, int64_t n, const float* s, int64_t m,
   PLIP_REQUIRE(n > 0 && m > 0, "similarity_topk: empty operand");
   PLIP_REQUIRE(k >= 1 && k <= kTopkMax, "similarity_topk: k=%d out of range [1,%d]", k, kTopkMax);
   PLIP_REQUIRE(n <= 0x7fffffff && m <= 0x7fffffff, "similarity_topk: operand too large");
+  static const int topk_simt = [] { const char* v = getenv("PLIP_SIM_SIMT"); return (v && v[0] == '1') ? 1 : 0; }();
+  if (!topk_simt && n >= 256 && m >= 8192)  // big retrieval problems: scores from the tensor cores, chunk by chunk
+    return launch_similarity_topk_tc(q, n, s, m, scale, norm_q, norm_s, k, idx, val, st);
   if (n * m < (int64_t)1 << 16) {
     // tiny problems (e.g. a handful of class prompts): one CTA per query streaming the space
     PLIP_CUDA_CHECK(launch_kernel(similarity_topk_kernel, dim3((unsigned)n), dim3(kTopkThreads), 0, st, 1, q, n, s, m,

@@ -59,6 +59,29 @@ def _check_ids(input_ids, attention_mask) -> Tuple[int, int]:
     return n, s
 
 
+@torch.no_grad()
+def similarity_topk(query: torch.Tensor, space: torch.Tensor, k: int, scale: float = 1.0, normalize_query: bool = True,
+                    normalize_space: bool = False, device: Union[int, str, torch.device, None] = None):
+    """``plip_similarity_topk`` needs no engine handle (no weights involved): fused scores + top-k over ``space`` rows on
+    ``device`` (default: the current CUDA device).  Returns ``(idx int32 [n,k], val f32 [n,k])``, best first."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("plip_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    L = lib()
+    q = query.to(torch.float32).to(dev, non_blocking=True).contiguous()
+    s = space.to(torch.float32).to(dev, non_blocking=True).contiguous()
+    n = int(q.shape[0])
+    idx = torch.empty(n, k, device=dev, dtype=torch.int32)
+    val = torch.empty(n, k, device=dev, dtype=torch.float32)
+    if n == 0:
+        return idx, val
+    with torch.cuda.device(dev):
+        check(L.plip_similarity_topk(q.data_ptr(), n, s.data_ptr(), int(s.shape[0]), C.c_float(scale), int(normalize_query),
+                                     int(normalize_space), int(k), idx.data_ptr(), val.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream), "plip_similarity_topk")
+    return idx, val
+
+
 class Engine:
     """One engine per CUDA device: packed bf16/fp32 weights + workspace for ``max_micro_batch``."""
 
@@ -188,18 +211,7 @@ class Engine:
     def similarity_topk(self, query: torch.Tensor, space: torch.Tensor, k: int, scale: float = 1.0,
                         normalize_query: bool = True, normalize_space: bool = False):
         """Fused scores + top-k over ``space`` rows: returns ``(idx int32 [n,k], val f32 [n,k])``, descending."""
-        q = self._dev(query.to(torch.float32))
-        s = self._dev(space.to(torch.float32))
-        n = int(q.shape[0])
-        idx = torch.empty(n, k, device=self.device, dtype=torch.int32)
-        val = torch.empty(n, k, device=self.device, dtype=torch.float32)
-        if n == 0:
-            return idx, val
-        with torch.cuda.device(self.device):
-            check(self._L.plip_similarity_topk(q.data_ptr(), n, s.data_ptr(), int(s.shape[0]), C.c_float(scale),
-                                               int(normalize_query), int(normalize_space), int(k), idx.data_ptr(),
-                                               val.data_ptr(), self._stream()), "plip_similarity_topk")
-        return idx, val
+        return similarity_topk(query, space, k, scale, normalize_query, normalize_space, device=self.device)
 
     @torch.no_grad()
     def l2_normalize_(self, x: torch.Tensor) -> torch.Tensor:

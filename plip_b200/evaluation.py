@@ -14,21 +14,30 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 import torch
 
-from .engine import Engine
+from .engine import Engine, similarity_topk
 
 
 def _t(x) -> torch.Tensor:
     return x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
 
 
-class ZeroShotClassifier:
-    def __init__(self, engine: Engine):
+class _Head:
+    """Constructible with no arguments like the reference's classes (``zero_shot.py:7-8``, ``retrieval.py:6-7``): the
+    similarity kernels need no weights, only a device — the current CUDA device, or that of an ``engine`` if given."""
+
+    def __init__(self, engine: Optional[Engine] = None):
         self.engine = engine
+
+    def _topk(self, query, space, k):
+        dev = self.engine.device if self.engine is not None else None
+        return similarity_topk(query, space, k, scale=1.0, normalize_query=False, normalize_space=False, device=dev)
+
+
+class ZeroShotClassifier(_Head):
 
     def predict(self, image_embeddings, text_embeddings, unique_labels: Sequence) -> List:
         """``[unique_labels[np.argmax(i)] for i in image_embeddings.dot(text_embeddings.T)]`` (zero_shot.py:12-13)."""
-        idx, _ = self.engine.similarity_topk(_t(image_embeddings), _t(text_embeddings), 1, scale=1.0,
-                                             normalize_query=False, normalize_space=False)
+        idx, _ = self._topk(_t(image_embeddings), _t(text_embeddings), 1)
         return [unique_labels[i] for i in idx[:, 0].cpu().tolist()]
 
     def zero_shot_classification(self, image_embeddings, text_embeddings, unique_labels, target_labels,
@@ -51,16 +60,14 @@ def retrieval_metrics(y_target, y_predictions):
     return {"p@10": p10 / len(y_target), "p@50": p50 / len(y_target)}
 
 
-class ImageRetrieval:
-    def __init__(self, engine: Engine):
-        self.engine = engine
+class ImageRetrieval(_Head):
 
     def best_scores(self, image_embeddings, text_embeddings, top_k: int = 50) -> np.ndarray:
         """Per text query, indices of the ``top_k`` most similar images, best first
         (``t.dot(image_embeddings.T).argsort()[-50:][::-1]``, retrieval.py:13-16)."""
         imgs, txt = _t(image_embeddings), _t(text_embeddings)
         k = min(top_k, imgs.shape[0])
-        idx, _ = self.engine.similarity_topk(txt, imgs, k, scale=1.0, normalize_query=False, normalize_space=False)
+        idx, _ = self._topk(txt, imgs, k)
         return idx.cpu().numpy()
 
     def retrieval(self, image_embeddings, text_embeddings):

@@ -245,7 +245,8 @@ def test_similarity_and_topk(L):
     assert (y - x / x.norm(dim=-1, keepdim=True)).abs().max().item() < 1e-6
 
 
-@pytest.mark.parametrize("n,m,k", [(200, 3000, 50), (1000, 777, 10), (3, 40000, 64), (130, 64, 1)])
+@pytest.mark.parametrize("n,m,k", [(200, 3000, 50), (1000, 777, 10), (3, 40000, 64), (130, 64, 1),
+                                   (300, 20000, 50), (257, 8192, 10)])   # the last two: tensor-core score chunks + row merge
 def test_similarity_topk_tiled(L, n, m, k):
     """GEMM-shaped fused top-k (never materialises [n,m]) == torch.topk of the full fp32 score matrix."""
     dev = "cuda"

@@ -246,9 +246,10 @@ def test_evaluation_heads(engine):
     txt = img[:120] + 0.05 * rng.standard_normal((120, 512)).astype(np.float32)     # query i matches image i
     labels = [f"c{i}" for i in range(7)]
     cls_emb = rng.standard_normal((7, 512)).astype(np.float32)
-    preds = ZeroShotClassifier(engine).predict(img, cls_emb, labels)
+    assert ZeroShotClassifier().predict(img, cls_emb, labels) == ZeroShotClassifier(engine).predict(img, cls_emb, labels)
+    preds = ZeroShotClassifier().predict(img, cls_emb, labels)       # zero-argument constructor, as the reference's
     assert preds == [labels[int(np.argmax(r))] for r in img.dot(cls_emb.T)]          # zero_shot.py:12-13
-    best = ImageRetrieval(engine).best_scores(img, txt)
+    best = ImageRetrieval().best_scores(img, txt)
     ref = np.stack([t.dot(img.T).argsort()[-50:][::-1] for t in txt])                # retrieval.py:13-16
     assert np.array_equal(best, ref)
     train, test = ImageRetrieval(engine).retrieval(img[:120], txt)
