@@ -45,7 +45,9 @@ struct Cfg {
   static constexpr uint32_t STAGE = A_STAGE + B_STAGE;
   static constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   // per-warp staging blocks + per-warp bias slice (+ colsum slice for the LN fold): a warp owns BN / 2 columns
-  static constexpr uint32_t VEC_BYTES = (LN_FOLD ? 2 : 1) * (BN / 2) * 4;  // per warp
+  // (a warp's share is the larger half of the tile's 64-column blocks: BN = 192 splits 2 + 1)
+  static constexpr int VEC_FLOATS = ((BN / 64 + 1) / 2) * 64;
+  static constexpr uint32_t VEC_BYTES = (LN_FOLD ? 2 : 1) * VEC_FLOATS * 4;  // per warp
   static constexpr uint32_t EPI_BYTES = kEpiWarps * 32 * 128 + kEpiWarps * VEC_BYTES;
   static constexpr uint32_t BAR_BYTES = 256;
   // The dynamic smem window starts 1024-aligned (checked at kernel entry), so no alignment slack is
@@ -95,7 +97,7 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 
 // acc (+ bias from the smem bias tile) for 32 consecutive columns of this thread's row, as 16 float2 (packed fp32 math).
 // LN_FOLD: rstd * acc + (bias' - (rstd * mean) * colsum)  ==  rstd * (acc - mean * colsum) + bias'; the warp's colsum
-// slice is stored BN / 2 floats after its bias slice.  `nrm` = -rstd * mean.
+// slice is stored Cfg::VEC_FLOATS floats after its bias slice.  `nrm` = -rstd * mean.
 template <bool HAS_BIAS, bool LN_FOLD, int BN>
 __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, float nrm, float rstd,
                                            float2 (&f)[16]) {
@@ -110,7 +112,7 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, f
     const float2 a0 = make_float2(__uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]));
     const float2 a1 = make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
     if constexpr (LN_FOLD) {
-      const float4 cs = ld_shared_f4(bias_smem + (BN / 2) * 4 + 16 * i);
+      const float4 cs = ld_shared_f4(bias_smem + (((BN / 64 + 1) / 2) * 64) * 4 + 16 * i);
       f[2 * i + 0] = __ffma2_rn(rstd2, a0, __ffma2_rn(nrm2, make_float2(cs.x, cs.y), make_float2(b.x, b.y)));
       f[2 * i + 1] = __ffma2_rn(rstd2, a1, __ffma2_rn(nrm2, make_float2(cs.z, cs.w), make_float2(b.z, b.w)));
     } else if constexpr (HAS_BIAS) {
@@ -424,17 +426,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int t = tile0; t < num_tiles; t += tile_step) {
       const int m_blk = t / num_n_blk, n_blk = t - m_blk * num_n_blk;
       if constexpr (HAS_BIAS) {
-        // this warp's slice of the bias (and colsum) vector: the BN / 2 columns it will touch, in its own order
+        // this warp's slice of the bias (and colsum) vector: the (about BN / 2) columns it will touch, in its own order
         // (column blocks half, half + 2, ... of W columns).  Private to the warp: __syncwarp instead of a 256-thread
         // barrier per tile (ncu r2b: "barrier" was the second stall reason of every epilogue).
         constexpr bool kOut16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || LN_FOLD);
         constexpr int W = kOut16 ? 64 : 32;
         float* bs = reinterpret_cast<float*>(smem_raw + (bias_base - smem_raw_u32) + warp * C::VEC_BYTES);
         __syncwarp();
-        for (int i = lane; i < BN / 2; i += 32) {
-          const int col = n_blk * BN + (half + 2 * (i / W)) * W + (i % W);
-          bs[i] = __ldg(p.bias + col);
-          if constexpr (LN_FOLD) bs[BN / 2 + i] = __ldg(p.colsum + col);
+        for (int i = lane; i < C::VEC_FLOATS; i += 32) {
+          const int cb = (half + 2 * (i / W)) * W + (i % W);       // column inside the tile
+          if (cb < BN) {
+            bs[i] = __ldg(p.bias + n_blk * BN + cb);
+            if constexpr (LN_FOLD) bs[C::VEC_FLOATS + i] = __ldg(p.colsum + n_blk * BN + cb);
+          }
         }
         __syncwarp();
       }
