@@ -6,22 +6,20 @@
 // vision S = 50 without mask, text S <= 77 with the causal (+ key padding) mask (TF:546-557).
 // The dh^-0.5 = 0.125 scale is folded into the q rows of the packed QKV weights (exact: power of 2).
 //
-// Sequences are short, so G = floor(128 / S) consecutive sequences of one head are packed into one
-// 128-row UMMA tile (vision: 2 images = 100 rows; text: 1 caption = 77 rows) and attention between
-// different sequences is masked out (block-diagonal), which keeps the arithmetic exact:
-//   TMA      Q,K,V head slices [128 rows x 64] of the QKV activation -> smem (128B swizzle)
+// Sequences are short, so G = 128 / slot sequences of one head share a 128-row UMMA tile, slot = 32 / 64 / 128 rows
+// (the power of two >= S), and attention between different sequences is masked out (block-diagonal: exact):
+//   TMA      per sequence a [slot x 64] box of the Q, K, V head slices of the QKV activation -> smem (128B swizzle)
 //   MMA 1    S[128x128] (TMEM, fp32) = Q (smem, K-major) x K^T (smem, K-major)         4 x UMMA 128x128x16
-//   softmax  thread == query row: tcgen05.ld S, mask, max, exp2, row sum; P (bf16) -> TMEM via tcgen05.st
+//   softmax  thread == query row, a warp == one sequence: tcgen05.ld only that sequence's chunks, mask, max, exp2,
+//            row sum; P (16-bit) -> TMEM via tcgen05.st
 //   MMA 2    O[128x64] (TMEM, fp32) = P (TMEM, A operand) x V (smem, MN-major)          8 x UMMA 128x64x16
-//   epilogue tcgen05.ld O, multiply by 1/rowsum, bf16 -> global (head slice of the [rows, D] output)
+//   epilogue tcgen05.ld O, multiply by 1/rowsum, 16-bit -> V buffer -> one TMA bulk store per sequence
 // 5 warps: warps 0-3 = softmax/epilogue (one TMEM lane quarter each), warp 4 = TMA + MMA issuer.
-// TMEM: 128 columns per CTA — P (bf16 pairs, 64 cols) is written in place over the S columns a thread
+// TMEM: 128 columns per CTA — P (16-bit pairs, 64 cols) is written in place over the S columns a thread
 // has already consumed, O (64 cols) reuses the upper half of S.  With single Q/K and V smem buffers
-// (48 KB; the next tile's Q,K are fetched as soon as MMA 1 retires, its V as soon as MMA 2 retires)
+// (48 KB; the next tile's Q,K are fetched as soon as MMA 1 retires, its V once the output store has read the buffer)
 // four CTAs co-reside per SM and hide each other's serial load -> MMA -> softmax -> MMA -> store chain.
 #include "kernels.cuh"
-
-#include <stdlib.h>
 
 namespace plip {
 
@@ -42,246 +40,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
-      "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
-      "r"(v[15])
-      : "memory");
-}
-
-struct AttParams {
-  int64_t total_rows;   // n_seq * seq_len
-  int seq_len;          // S
-  int group;            // G sequences per tile
-  int rows_per_tile;    // R = G * S
-  int heads;
-  int64_t seq_tiles;    // ceil(n_seq / G)
-  int causal;
-  const int32_t* key_mask;  // [n_seq, S] or nullptr
-  __nv_bfloat16* out;       // [total_rows, heads*64]
-};
-
-__global__ void __launch_bounds__(kAttThreads, kAttCtasPerSm)
-attention_kernel_v1(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_raw_u32 = smem_u32(smem_raw);
-  const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStageBytes;
-  const uint32_t bar_qk = bar_base, bar_v = bar_base + 8;
-  const uint32_t bar_s = bar_base + 16, bar_p = bar_base + 24, bar_o = bar_base + 32, bar_e = bar_base + 40;
-  const uint32_t tmem_slot = bar_base + 48;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int D = p.heads * kHeadDim;
-
-  if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&tmQKV);
-    mbar_init(bar_qk, 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
-    mbar_init(bar_o, 1);
-    mbar_init(bar_e, 128);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc<1>(tmem_slot, kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base =
-      *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
-
-  const int64_t num_tiles = p.seq_tiles * p.heads;
-
-  if (warp == 4) {
-    // ===================== TMA producer + MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S = Q K^T, both K-major
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // O = P V, V is MN-major
-      const uint32_t sq = smem_base, sk = smem_base + kTileBytes, sv = smem_base + 2 * kTileBytes;
-      auto coords = [&](int64_t tile, int& h, int32_t& row0) {
-        const int64_t st = tile / p.heads;
-        h = (int)(tile - st * p.heads);
-        row0 = (int32_t)(st * p.rows_per_tile);
-      };
-      auto issue_qk = [&](int64_t tile) {
-        int h; int32_t row0;
-        coords(tile, h, row0);
-        mbar_arrive_expect_tx(bar_qk, 2 * kTileBytes);
-        tma_load_2d(sq, &tmQKV, bar_qk, h * kHeadDim, row0);
-        tma_load_2d(sk, &tmQKV, bar_qk, D + h * kHeadDim, row0);
-      };
-      auto issue_v = [&](int64_t tile) {
-        int h; int32_t row0;
-        coords(tile, h, row0);
-        mbar_arrive_expect_tx(bar_v, kTileBytes);
-        tma_load_2d(sv, &tmQKV, bar_v, 2 * D + h * kHeadDim, row0);
-      };
-      int64_t tile = blockIdx.x;
-      if (tile < num_tiles) { issue_qk(tile); issue_v(tile); }
-      uint32_t it = 0;
-      const uint64_t qdesc = make_smem_desc_sw128(sq, 1024, 16);
-      const uint64_t kdesc = make_smem_desc_sw128(sk, 1024, 16);
-      for (; tile < num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t par = it & 1u;
-        const int64_t next = tile + gridDim.x;
-        mbar_wait(bar_qk, par);
-        if (it > 0) mbar_wait(bar_e, par ^ 1u);  // previous tile's O (aliases S) has been read out
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss<1>(tmem_base + kColS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit<1>(bar_s);
-        mbar_wait(bar_s, par);                   // MMA 1 retired: Q/K buffers are free
-        if (next < num_tiles) issue_qk(next);
-        mbar_wait(bar_p, par);                   // softmax warps published P in TMEM
-        mbar_wait(bar_v, par);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // V tile [128 keys][64 dh]: advancing 16 keys (one UMMA K) = 16 rows of 128 B
-          const uint64_t vdesc = make_smem_desc_sw128(sv + k * 2048, 1024, 1024);
-          umma_ts(tmem_base + kColO, tmem_base + kColP + k * 8, vdesc, idesc_o, k != 0 ? 1u : 0u);
-        }
-        umma_commit<1>(bar_o);
-        mbar_wait(bar_o, par);                   // MMA 2 retired: V buffer is free
-        if (next < num_tiles) issue_v(next);
-      }
-    }
-  } else {
-    // ===================== softmax + epilogue (thread == query row) =====================
-    const int r = threadIdx.x;  // 0..127 == TMEM lane
-    const int S = p.seq_len;
-    const int seq_r = r / S;
-    const int pos_r = r - seq_r * S;
-    const bool row_in_tile = r < p.rows_per_tile;
-    const int c_lo = seq_r * S;
-    const int c_hi = row_in_tile ? (c_lo + (p.causal ? pos_r + 1 : S)) : c_lo;  // empty range for pad rows
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    constexpr float kLog2e = 1.4426950408889634f;
-
-    uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int64_t st = tile / p.heads;
-      const int h = (int)(tile - st * p.heads);
-      const int64_t row0 = st * p.rows_per_tile;
-
-      // per-chunk validity masks (bit c = key column 32*j + c may be attended by this row)
-      uint32_t valid[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int lo = max(c_lo - 32 * j, 0), hi = min(c_hi - 32 * j, 32);
-        uint32_t m = 0;
-        if (hi > lo) m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-        if (p.key_mask != nullptr) {
-          const int c = 32 * j + lane;
-          const int64_t grow = row0 + c;
-          const bool kv = (c < p.rows_per_tile) && (grow < p.total_rows) && (p.key_mask[grow] != 0);
-          m &= __ballot_sync(0xffffffffu, kv);
-        }
-        valid[j] = m;
-      }
-
-      mbar_wait(bar_s, it & 1u);
-      tc_fence_after();
-
-      // pass 1: row maximum over the valid columns
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        if (__any_sync(0xffffffffu, valid[j] != 0)) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + kColS + 32 * j, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if ((valid[j] >> c) & 1u) mx = fmaxf(mx, __uint_as_float(v[c]));
-        }
-      }
-      const float mx_s = (mx == -INFINITY) ? 0.f : mx * kLog2e;
-
-      // pass 2: p = exp(s - max), row sum, P (bf16) -> TMEM
-      float sum = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        uint32_t pk[16];
-        if (__any_sync(0xffffffffu, valid[j] != 0)) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + kColS + 32 * j, v);
-          tmem_ld_wait();
-          const uint32_t vm = valid[j];
-          if (__all_sync(0xffffffffu, vm == 0xffffffffu)) {
-            // every column of this chunk is visible to every row of the warp: no masking work
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * c]), kLog2e, -mx_s));
-              const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * c + 1]), kLog2e, -mx_s));
-              sum += e0 + e1;
-              pk[c] = pack_bf16x2(e0, e1);
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * c]), kLog2e, -mx_s));
-              float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * c + 1]), kLog2e, -mx_s));
-              e0 = ((vm >> (2 * c)) & 1u) ? e0 : 0.f;
-              e1 = ((vm >> (2 * c + 1)) & 1u) ? e1 : 0.f;
-              sum += e0 + e1;
-              pk[c] = pack_bf16x2(e0, e1);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) pk[c] = 0u;
-        }
-        tmem_st16(lane_base + kColP + 16 * j, pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(bar_p);
-
-      // epilogue: O / rowsum -> bf16 head slice
-      mbar_wait(bar_o, it & 1u);
-      tc_fence_after();
-      const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-      const int64_t grow = row0 + r;
-      const bool store = row_in_tile && grow < p.total_rows;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint32_t v[32];
-        tmem_ld32(lane_base + kColO + 32 * j, v);
-        tmem_ld_wait();
-        if (j == 1) {  // O fully read: the next tile's S = Q K^T may overwrite these columns
-          tc_fence_before();
-          mbar_arrive(bar_e);
-        }
-        if (store) {
-          uint4* o4 = reinterpret_cast<uint4*>(p.out + grow * D + h * kHeadDim + 32 * j);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
-            o4[q] = u;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<1>(tmem_base, kTmemCols);
-}
-
 // =====================================================================================================
-// v2 (round 2).  ncu on v1: ALU pipe 46 % busy, DRAM 38 %, tensor 14 % — the kernel was bound by the INSTRUCTION
+// Round-2 design notes.  ncu on the round-1 kernel (one 128-row tile = floor(128 / S) sequences back to back, two-pass
+// softmax over all four chunks, row stores): ALU pipe 33 %, DRAM 42 %, tensor 16 % — it was bound by the INSTRUCTION
 // COUNT of the softmax (per-element bit tests in two passes over up to four 32-column chunks, most of them
 // belonging to the other sequence of the tile) and by 32-line-per-instruction row stores.  Changes:
 //   * slot layout: a tile holds G = 128 / slot sequences, slot = 32 / 64 / 128 rows (the power of two >= S), each
@@ -295,7 +56,7 @@ attention_kernel_v1(const __grid_constant__ CUtensorMap tmQKV, const AttParams p
 //     leaves with one TMA bulk store per sequence (box [S x 64]) instead of 8 x 32-line STG.128 per warp; the
 //     next tile's V load waits for that store to have read the buffer (bar_vfree).
 // =====================================================================================================
-struct AttParams2 {
+struct AttParams {
   int64_t total_rows;   // n_seq * seq_len
   int64_t n_seq;
   int seq_len;          // S
@@ -353,10 +114,10 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float mx) {
   return mx;
 }
 
-template <int CTAS, bool F16>
-__global__ void __launch_bounds__(kAttThreads, CTAS)
+template <bool F16>
+__global__ void __launch_bounds__(kAttThreads, kAttCtasPerSm)
 attention_kernel(const __grid_constant__ CUtensorMap tmLoad, const __grid_constant__ CUtensorMap tmStore,
-                 const AttParams2 p) {
+                 const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (smem_raw_u32 + 1023u) & ~1023u;
@@ -594,46 +355,18 @@ int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int h
   PLIP_REQUIRE(heads > 0 && heads <= 16, "attention: bad head count %d", heads);
   static unsigned long long configured = 0;
   static int grid_cap = 0;
-  static int use_v1 = 0, ctas = kAttCtasPerSm;
   if (first_use_on_device(configured)) {
-    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmem));
-    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmem));
-    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmem));
-    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kAttSmem));
+    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmem));
+    PLIP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttSmem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const char* v = getenv("PLIP_ATT_V1");  // A/B switch for the round-1 kernel (removed once v2 is validated)
-    use_v1 = (v != nullptr && v[0] == '1') ? 1 : 0;
-    const char* c = getenv("PLIP_ATT_CTAS");  // 3 = 128 registers per thread (no spills), 4 = 96
-    if (c != nullptr && c[0] == '3' && !use_v1) ctas = 3;
-    grid_cap = ctas * sms;
+    grid_cap = kAttCtasPerSm * sms;
   }
   const int D = heads * kHeadDim;
   const int64_t rows = n_seq * seq_len;
   PLIP_REQUIRE(rows + 128 < 0x7fffffff, "attention: too many token rows");
-  PLIP_REQUIRE(!(f16 && (use_v1 || ctas == 3)), "attention: the fp16 operand format runs on the default kernel only");
-  if (use_v1) {
-    CUtensorMap tm;
-    if (int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)rows, (uint64_t)3 * D, (uint64_t)3 * D * 2, 128, 64)) return rc;
-    AttParams p;
-    p.total_rows = rows;
-    p.seq_len = seq_len;
-    p.group = 128 / seq_len;
-    p.rows_per_tile = p.group * seq_len;
-    p.heads = heads;
-    p.seq_tiles = (n_seq + p.group - 1) / p.group;
-    p.causal = causal ? 1 : 0;
-    p.key_mask = key_mask;
-    p.out = out;
-    const int64_t tiles = p.seq_tiles * heads;
-    const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
-    PLIP_CUDA_CHECK(launch_kernel(attention_kernel_v1, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tm, p));
-    ++g_launch_count;
-    return 0;
-  }
-  AttParams2 p;
+  AttParams p;
   p.total_rows = rows;
   p.n_seq = n_seq;
   p.seq_len = seq_len;
@@ -648,9 +381,8 @@ int launch_attention(const __nv_bfloat16* qkv, int64_t n_seq, int seq_len, int h
   if (int rc = make_tmap_bf16_2d(&tmS, out, (uint64_t)rows, (uint64_t)D, (uint64_t)D * 2, (uint32_t)seq_len, 64)) return rc;
   const int64_t tiles = p.seq_tiles * heads;
   const int grid = (int)(tiles < grid_cap ? tiles : grid_cap);
-  if (ctas == 3) PLIP_CUDA_CHECK(launch_kernel(attention_kernel<3, false>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
-  else if (f16) PLIP_CUDA_CHECK(launch_kernel(attention_kernel<4, true>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
-  else PLIP_CUDA_CHECK(launch_kernel(attention_kernel<4, false>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
+  if (f16) PLIP_CUDA_CHECK(launch_kernel(attention_kernel<true>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
+  else PLIP_CUDA_CHECK(launch_kernel(attention_kernel<false>, dim3(grid), dim3(kAttThreads), kAttSmem, st, 1, tmL, tmS, p));
   ++g_launch_count;
   return 0;
 }
