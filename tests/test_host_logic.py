@@ -76,3 +76,26 @@ def test_shard_counts_and_ranges():
     assert D.world() == (0, 1)
     x = torch.arange(6.).view(3, 2)
     assert D.all_gather_rows(x) is x   # single process: identity
+
+
+def test_non_rgb_images_follow_the_openai_transform_order():
+    """reproducibility/embedders/transform.py:45-52 resizes and crops BEFORE convert("RGB"): for palette / bilevel
+    images Pillow then resamples with NEAREST, for RGBA / LA it resamples premultiplied — converting first (what the
+    HF processor of plip.py does, and what the RGB fast path does) would give different tiles."""
+    import numpy as np
+    import PIL.Image
+    from plip_b200.preprocess import decode_native_then_rgb, resize_plan
+
+    rng = np.random.default_rng(3)
+    pal = PIL.Image.fromarray(rng.integers(0, 256, (260, 300), dtype=np.uint8), mode="P")
+    pal.putpalette(rng.integers(0, 256, 768, dtype=np.uint8).tobytes())
+    rgba = PIL.Image.fromarray(rng.integers(0, 256, (300, 250, 4), dtype=np.uint8), mode="RGBA")
+    rgb = PIL.Image.fromarray(rng.integers(0, 256, (240, 320, 3), dtype=np.uint8))
+    got = decode_native_then_rgb([pal, rgba, rgb], crop="round")
+    for im, out in zip((pal, rgba), got[:2]):
+        nw, nh, left, top = resize_plan(*im.size, 224, "round")
+        ref = im.resize((nw, nh), resample=PIL.Image.BICUBIC).crop((left, top, left + 224, top + 224)).convert("RGB")
+        assert out.shape == (224, 224, 3) and np.array_equal(out, np.asarray(ref))
+        first = np.asarray(im.convert("RGB").resize((nw, nh), resample=PIL.Image.BICUBIC).crop((left, top, left + 224, top + 224)))
+        assert not np.array_equal(out, first)                        # the order really matters for these modes
+    assert got[2].shape == (240, 320, 3)                             # RGB images stay un-resized for the device kernel
