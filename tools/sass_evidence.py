@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Per-kernel counts of the Blackwell-native SASS mnemonics in the built library (no GPU needed).
+
+    python tools/sass_evidence.py > profiles/r2_sass_evidence.txt
+"""
+import collections
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WANT = ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UTCBAR", "UTCATOMSWS", "SYNCS", "UCGABAR_ARV",
+        "UCGABAR_WAIT", "FFMA2", "FMUL2", "FADD2", "HMMA", "MUFU.TANH", "MUFU.EX2")
+
+
+def demangle(names):
+    out = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.split("\n")
+    return dict(zip(names, out))
+
+
+def main():
+    sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "plip_b200", "libplip_b200.so")], capture_output=True, text=True).stdout
+    cur, counts = None, collections.OrderedDict()
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            counts[cur] = collections.Counter()
+            continue
+        if cur is None:
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\w+\s+)?([A-Z][A-Z0-9_.]*)", line)
+        if m:
+            op = m.group(1)
+            for w in WANT:
+                if op == w or op.startswith(w + "."):
+                    counts[cur][w] += 1
+    names = demangle(list(counts))
+    print("# SASS evidence (cuobjdump -sass plip_b200/libplip_b200.so, sm_100a), round 2: Blackwell-native instructions per kernel")
+    print("# UTCHMMA = tcgen05.mma kind::f16, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA tensor load/store, UTCBAR = tcgen05.commit,")
+    print("# UTCATOMSWS = tcgen05.alloc/dealloc, SYNCS = mbarrier ops, UCGABAR = cluster barrier, FFMA2/FMUL2/FADD2 = packed fp32 (fma.rn.f32x2 ...);")
+    print("# no HMMA (legacy mma.sync) anywhere.  gemm_kernel<CTA group, BLOCK_N, epilogue, fp16 operands>: epilogues 0 bias, 1 bias+GELU,")
+    print("# 2 bias+residual, 3 patch, 4 f32, 5/6 LN-folded 0/1, 7 null, 8 similarity (row x column scales)")
+    print()
+    seen = set()
+    for k, c in counts.items():
+        if not c:
+            continue
+        short = names[k].replace("plip::(anonymous namespace)::", "").replace("void ", "")
+        short = re.sub(r"\((?:[^()]|\([^()]*\))*\)$", "", short.strip())
+        if "<1, " in short and "gemm_kernel" in short:   # single-CTA variants: test hooks only
+            continue
+        if short in seen:
+            continue
+        seen.add(short)
+        print(f"{short}: " + ", ".join(f"{w} x{c[w]}" for w in WANT if c[w]))
+    tot = collections.Counter()
+    for c in counts.values():
+        tot.update(c)
+    print()
+    print("totals: " + ", ".join(f"{w} x{tot[w]}" for w in WANT))
+
+
+if __name__ == "__main__":
+    main()
