@@ -775,7 +775,9 @@ PLIP_API int plip_encode_text_prefix(plip_engine_t* e, const void* ids_dev, int 
   PLIP_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_last, 0));
   const size_t isz = ids_dtype == PLIP_IDS_I64 ? 8 : 4;
   if (graph_eligible(e, n)) {
-    const auto key = std::make_tuple(1, (int)n, ids_dtype, normalize ? 1 : 0, seq_len, prefix_len, attention_mask_dev ? 1 : 0);
+    // everything a captured launch sequence bakes in is part of the key (incl. the pooling convention)
+    const auto key = std::make_tuple(1 + 2 * e->text_pool_argmax, (int)n, ids_dtype, normalize ? 1 : 0, seq_len, prefix_len,
+                                     attention_mask_dev ? 1 : 0);
     const size_t ib = (size_t)n * seq_len * isz;
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
