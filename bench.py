@@ -832,8 +832,10 @@ def bench_cfg5(ctx):
     clocks = sampler.stop(t0, t1) if sampler else None
     # the similarity block and the fused top-k head alone
     gal, q_all = state["gal"], state["q_all"]
-    ms_sim = timer.timed(lambda i: sh.similarity(gal, q_all, sh.logit_scale_exp), 2) / 2
-    ms_topk = timer.timed(lambda i: sh.retrieval_topk(gal, q_all, 50, n_gal), 2) / 2
+    sh.similarity(gal, q_all, sh.logit_scale_exp)
+    sh.retrieval_topk(gal, q_all, 50, n_gal)                      # untimed first calls: scratch growth, lazy module loading
+    ms_sim = timer.timed(lambda i: sh.similarity(gal, q_all, sh.logit_scale_exp), 3) / 3
+    ms_topk = timer.timed(lambda i: sh.retrieval_topk(gal, q_all, 50, n_gal), 3) / 3
     # e2e: gallery micro-batches uploaded from a pinned host ring inside the timed region; top-50 per query returned
     ring = [torch.from_numpy(synth.tiles_u8(PAIRS, seed=100 + rank + i)).pin_memory() for i in range(2)]
     top_h = torch.empty(n_q, 50, dtype=torch.int64).pin_memory()
@@ -851,6 +853,7 @@ def bench_cfg5(ctx):
         top_h.copy_(idx, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    e2e_step(0)
     ms_e2e = timer.timed(e2e_step, max(1, args.steps // 2))
     if rank != 0:
         return 0
@@ -866,8 +869,8 @@ def bench_cfg5(ctx):
              "similarity_block": {"shape": [n_local, n_q], "ms": ms_sim, "tflops_fp32": sim_flop / ms_sim / 1e9,
                                   "write_GBps": n_local * n_q * 4 / ms_sim / 1e6,
                                   "frac_of_hbm_peak": n_local * n_q * 4 / ms_sim / 1e6 / peaks["hbm_gbs"]},
-             "fused_topk50_merge": {"ms": ms_topk, "note": "local fused top-50 of all queries over this rank's gallery rows + "
-                                                           "all-gather of candidates + merge (retrieval.py:13-16 semantics)"}}
+             "fused_topk50_merge": {"ms": ms_topk, "note": "top-50 of all queries over this rank's gallery rows (tensor-core score chunks + "
+                                                           "row merge) + all-gather of candidates + merge (retrieval.py:13-16 semantics)"}}
     emit(ctx, n_gal * args.steps / (ms / 1e3), unit, metric, ms / args.steps, args.steps, "strong", clocks, e2e, launches, None, extra)
     return 0
 

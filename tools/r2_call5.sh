@@ -15,4 +15,6 @@ python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2f_bench.json 2> gp
 python bench.py --config cfg3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2f_bench_cfg3.json 2> gpurun_out/r2f_bench_cfg3.err
 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 560 --csv --log-file gpurun_out/r2f_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --quick --no-cpu-baseline > gpurun_out/r2f_ncu_bench.log 2>&1
-cat gpurun_out/r2f_rc.txt
+TOPK_DUP=1 python tools/topk_probe.py > gpurun_out/r2f_topk_dup.log 2>&1
+python bench.py --config cfg5 --tiles 125000 --steps 2 --quick --no-cpu-baseline > gpurun_out/r2f_bench_cfg5_125k.json 2> gpurun_out/r2f_bench_cfg5_125k.err
+cat gpurun_out/r2f_rc.txt gpurun_out/r2f_topk_dup.log

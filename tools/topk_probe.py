@@ -15,6 +15,8 @@ q = torch.randn(n, 512, generator=g).cuda()
 s = torch.randn(m, 512, generator=g).cuda()
 q = q / q.norm(dim=1, keepdim=True)
 s = s / s.norm(dim=1, keepdim=True)
+if os.environ.get("TOPK_DUP"):      # a gallery drawn cyclically from 8192 distinct rows (what bench.py --config cfg5 uses): exact ties
+    s = s[:8192].repeat((m + 8191) // 8192, 1)[:m].contiguous()
 for _ in range(2):
     idx, val = similarity_topk(q, s, k, normalize_query=False)
 torch.cuda.synchronize()
