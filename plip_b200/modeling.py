@@ -125,10 +125,16 @@ class PlipCLIPModel:
         if not pixel_values.is_cuda:
             # host inputs (an extension: HF would raise on a device mismatch): the pixel upload runs on the engine's
             # copy stream while the text tower computes, so ~3 ms of PCIe time per 1024 uint8 tiles stay hidden
-            pixel_values, uploaded = self.engine.upload_async(pixel_values)
+            # ... and batches larger than one micro-batch are uploaded micro-batch by micro-batch, each one computed as
+            # soon as it has landed while the next one travels
+            mb = self.engine.max_micro_batch
+            parts = [self.engine.upload_async(pixel_values[i:i + mb]) for i in range(0, pixel_values.shape[0], mb)]
             txt = self.engine.encode_text(input_ids, attention_mask, normalize=True)
-            torch.cuda.current_stream(self.device).wait_event(uploaded)
-            img = self.engine.encode_images(pixel_values, normalize=True)
+            embs = []
+            for chunk, uploaded in parts:
+                torch.cuda.current_stream(self.device).wait_event(uploaded)
+                embs.append(self.engine.encode_images(chunk, normalize=True))
+            img = embs[0] if len(embs) == 1 else torch.cat(embs, dim=0)
         else:
             img = self.engine.encode_images(pixel_values, normalize=True)
             txt = self.engine.encode_text(input_ids, attention_mask, normalize=True)
