@@ -179,6 +179,21 @@ def test_small_batch_graph_replay_is_bit_identical(engine, state_dict):
     assert (1 - O.cosine(engine.encode_images(px[:3]).cpu(), e1[:3].cpu())).max().item() < 1e-6   # another n / graph
 
 
+def test_forward_on_host_inputs_equals_device_inputs(state_dict):
+    """`model(**inputs)` with HOST tensors (the e2e path of bench.py): pixels are uploaded micro-batch by micro-batch on
+    the engine's copy stream while the text tower / the previous micro-batch computes — same logits, bit for bit."""
+    from plip_b200.modeling import PlipCLIPModel
+    model = PlipCLIPModel(state_dict, max_micro_batch=64)
+    tiles = torch.from_numpy(synth.tiles_u8(150, seed=61))
+    ids = synth.token_ids(20, seed=62)[0]
+    dev = model(input_ids=ids.cuda(), pixel_values=tiles.cuda())
+    host = model(input_ids=ids, pixel_values=tiles.pin_memory())
+    host2 = model(input_ids=ids, pixel_values=tiles)                      # pageable source
+    assert host.logits_per_image.is_cuda and host.logits_per_image.shape == (150, 20)
+    assert torch.equal(dev.logits_per_image, host.logits_per_image) and torch.equal(dev.logits_per_image, host2.logits_per_image)
+    model.engine.close()
+
+
 def test_calls_on_different_streams_are_serialised(engine):
     """One handle = one workspace: back-to-back calls on different streams (and the host path right after a
     device call) must not corrupt each other."""
