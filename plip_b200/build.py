@@ -30,6 +30,9 @@ NVCC_FLAGS = [
 ]
 
 
+NVCC_FLAGS += os.environ.get("PLIP_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DPLIP_NO_RPF for an A/B build
+
+
 def _nvcc() -> str:
     cand = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not Path(cand).exists():

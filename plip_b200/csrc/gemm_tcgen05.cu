@@ -48,7 +48,16 @@ struct Cfg {
   // (a warp's share is the larger half of the tile's 64-column blocks: BN = 192 splits 2 + 1)
   static constexpr int VEC_FLOATS = ((BN / 64 + 1) / 2) * 64;
   static constexpr uint32_t VEC_BYTES = (LN_FOLD ? 2 : 1) * VEC_FLOATS * 4;  // per warp
-  static constexpr uint32_t EPI_BYTES = kEpiWarps * 32 * 128 + kEpiWarps * VEC_BYTES;
+  // Short-K residual GEMMs (out_proj: N tile 192 / 128) are paced by the fp32 read-modify-write of the residual tile,
+  // not by the MMAs: they double-buffer the residual blocks in shared memory with cp.async, one 32-column block ahead
+  // (and the first block of a tile while its MMAs still run), at the price of operand-ring stages they do not need.
+#ifdef PLIP_NO_RPF   // A/B build switch (tools/r2_call7.sh)
+  static constexpr bool RPF = false;
+#else
+  static constexpr bool RPF = (EPI == EPI_BIAS_RESID_F32) && (BN < 256);
+#endif
+  static constexpr uint32_t RPF_BYTES = RPF ? kEpiWarps * 2 * 4096 : 0;
+  static constexpr uint32_t EPI_BYTES = kEpiWarps * 32 * 128 + kEpiWarps * VEC_BYTES + RPF_BYTES;
   static constexpr uint32_t BAR_BYTES = 256;
   // The dynamic smem window starts 1024-aligned (checked at kernel entry), so no alignment slack is
   // reserved: that is what lets the residual epilogues run a 6-deep 32 KB operand ring.
@@ -95,6 +104,27 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One [32 rows x 32 fp32] block of the residual stream -> this warp's prefetch buffer: lane (rb_row, rb_chunk) copies
+// the eight 16-byte pieces it will read back itself (rows past M: zero fill), as one cp.async group.
+__device__ __forceinline__ void rpf_issue(const float* x, int ldo, int M, uint32_t buf, int row_base, int col0, int lane) {
+  const int rb_row = lane >> 3, rb_chunk = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rb_row;
+    const int grow = row_base + r;
+    const float* src = x + static_cast<size_t>(grow < M ? grow : 0) * ldo + col0 + rb_chunk * 4;
+    cp_async_16(buf + r * 128 + rb_chunk * 16, src, grow < M ? 16 : 0);
+  }
+  cp_async_commit();
+}
+
 // acc (+ bias from the smem bias tile) for 32 consecutive columns of this thread's row, as 16 float2 (packed fp32 math).
 // LN_FOLD: rstd * acc + (bias' - (rstd * mean) * colsum)  ==  rstd * (acc - mean * colsum) + bias'; the warp's colsum
 // slice is stored Cfg::VEC_FLOATS floats after its bias slice.  `nrm` = -rstd * mean.
@@ -129,8 +159,8 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, f
 template <int BN, int EPI, bool F16>
 __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMap* tmC, uint32_t tmem_row_base,
                                               uint32_t stage_smem,
-                                              uint32_t bias_smem, int row_base, int col_base, int n_blk, int half,
-                                              int lane, float ln_mean, float ln_rstd) {
+                                              uint32_t bias_smem, uint32_t rpf_smem, int row_base, int col_base, int n_blk,
+                                              int half, int lane, float ln_mean, float ln_rstd) {
   constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   constexpr bool GELU = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD);
@@ -219,15 +249,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
 #pragma unroll
     for (int i = 0; i < 8; ++i) st1[i] = st2[i] = 0.f;
     const bool emit = (EPI == EPI_BIAS_RESID_F32) && p.xb_out != nullptr;
+#ifdef PLIP_NO_RPF
+    constexpr bool RPF = false;
+#else
+    constexpr bool RPF = (EPI == EPI_BIAS_RESID_F32) && (BN < 256);  // == Cfg::RPF
+#endif
+    int jblk = 0;
 #pragma unroll 1
-    for (int blk = half; blk < BN / 32; blk += 2) {
+    for (int blk = half; blk < BN / 32; blk += 2, ++jblk) {
       // 32 columns -> 128 B of fp32 per row
       const int col = col_base + blk * 32 + rb_chunk * 4;
       float* out = reinterpret_cast<float*>(p.out);
+      const uint32_t rpf_cur = rpf_smem + static_cast<uint32_t>(jblk & 1) * 4096u;
+      const bool has_next = blk + 2 < BN / 32;
+      if constexpr (RPF) {
+        // block j sits (or is landing) in buffer j & 1 — the first one of the tile was issued before the accumulator
+        // wait; fetch block j + 1 into the other buffer (its last reader, block j - 1, ended with a __syncwarp)
+        if (has_next) rpf_issue(out, p.ldo, p.M, rpf_smem + static_cast<uint32_t>((jblk + 1) & 1) * 4096u, row_base, col_base + (blk + 2) * 32, lane);
+      }
       // Residual rows are fetched before the TMEM load / staging so their DRAM latency overlaps it
       // (issued back to back: a load->add->store chain per row serialises 8 round trips per block).
       float4 xr[8];
-      if constexpr (EPI == EPI_BIAS_RESID_F32) {
+      if constexpr (EPI == EPI_BIAS_RESID_F32 && !RPF) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int grow = row_base + i * 4 + rb_row;
@@ -243,12 +286,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
           st_shared_v4(my_row + ((c ^ sw) << 4), __float_as_uint(f[2 * c + 0].x), __float_as_uint(f[2 * c + 0].y),
                        __float_as_uint(f[2 * c + 1].x), __float_as_uint(f[2 * c + 1].y));
       }
+      if constexpr (RPF) {
+        if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();   // this block's residual rows have landed
+      }
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = i * 4 + rb_row;
         float4 v = ld_shared_f4(stage_smem + r * 128 + ((rb_chunk ^ (r & 7)) << 4));
         const int grow = row_base + r;
+        if constexpr (RPF) xr[i] = ld_shared_f4(rpf_cur + r * 128 + rb_chunk * 16);  // this lane's own copies
         if (grow < p.M) {
           if constexpr (EPI == EPI_BIAS_RESID_F32) {
             const float2 y01 = __fadd2_rn(make_float2(xr[i].x, xr[i].y), make_float2(v.x, v.y));
@@ -318,6 +365,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   const uint32_t epi_base = smem_base + STAGES * C::STAGE;   // 1024-aligned: 4 x 4 KB staging blocks
   const uint32_t bias_base = epi_base + kEpiWarps * kEpiStageBytes;  // per warp: BN / 2 bias (+ BN / 2 colsum) floats
+  const uint32_t rpf_base = bias_base + kEpiWarps * C::VEC_BYTES;    // per warp: 2 x 4 KB residual prefetch buffers (C::RPF)
   const uint32_t bar_base = smem_base + STAGES * C::STAGE + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -443,6 +491,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
       }
       const int row_base = m_blk * BM * CG + cta_rank * BM + q * 32;
+      if constexpr (C::RPF)  // first residual block of the tile -> prefetch buffer 0, while the MMAs of the tile run
+        rpf_issue(reinterpret_cast<const float*>(p.out), p.ldo, p.M, rpf_base + warp * 8192u, row_base, n_blk * BN + half * 32, lane);
       if constexpr (EPI == EPI_BIAS_RESID_F32) {
         // pull this warp's [32 rows x BN] slice of the residual stream into L2 while the MMAs run
         const float* xin = reinterpret_cast<const float*>(p.out);
@@ -484,7 +534,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      epilogue_tile<BN, EPI, F16>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + warp * C::VEC_BYTES, row_base,
+      epilogue_tile<BN, EPI, F16>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + warp * C::VEC_BYTES,
+                                  rpf_base + warp * 8192u, row_base,
                              n_blk * BN, n_blk, half, lane, ln_mean, ln_rstd);
       tc_fence_before();
       __syncwarp();
