@@ -51,8 +51,10 @@ struct Cfg {
   // Short-K residual GEMMs (out_proj: N tile 192 / 128) are paced by the fp32 read-modify-write of the residual tile,
   // not by the MMAs: they double-buffer the residual blocks in shared memory with cp.async, one 32-column block ahead
   // (and the first block of a tile while its MMAs still run), at the price of operand-ring stages they do not need.
-#ifdef PLIP_NO_RPF   // A/B build switch (tools/r2_call7.sh)
+#if defined(PLIP_NO_RPF)   // A/B build switches (tools/r2_call7.sh, r2_call8.sh)
   static constexpr bool RPF = false;
+#elif defined(PLIP_RPF_ALL)
+  static constexpr bool RPF = (EPI == EPI_BIAS_RESID_F32);
 #else
   static constexpr bool RPF = (EPI == EPI_BIAS_RESID_F32) && (BN < 256);
 #endif
@@ -249,8 +251,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
 #pragma unroll
     for (int i = 0; i < 8; ++i) st1[i] = st2[i] = 0.f;
     const bool emit = (EPI == EPI_BIAS_RESID_F32) && p.xb_out != nullptr;
-#ifdef PLIP_NO_RPF
+#if defined(PLIP_NO_RPF)
     constexpr bool RPF = false;
+#elif defined(PLIP_RPF_ALL)
+    constexpr bool RPF = (EPI == EPI_BIAS_RESID_F32);
 #else
     constexpr bool RPF = (EPI == EPI_BIAS_RESID_F32) && (BN < 256);  // == Cfg::RPF
 #endif
