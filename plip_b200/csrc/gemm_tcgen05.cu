@@ -684,9 +684,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     if (g.N % 192 == 0) bn = 192;
     else if (g.N == 512) bn = 128;  // text out_proj: 86.5 vs 91.8 us (exp14)
   }
-  static const int env_bn_fc2 = env_int("PLIP_GEMM_BN_FC2", 0);  // experiment: N tile of the long-K residual GEMM (fc2)
-  if (!g.force_bn && !env_bn && env_bn_fc2 && cg == 2 && g.epi == EPI_BIAS_RESID_F32 && g.K > 1024 && g.N % env_bn_fc2 == 0)
-    bn = env_bn_fc2;
+  // (192-wide tiles for the long-K residual GEMM, fc2, were measured slower in round 2: 252.9 vs 238.0 us in step)
   if (g.N % bn != 0) bn = 128;
   PLIP_REQUIRE((cg == 1 || cg == 2) && (bn == 128 || bn == 256 || (bn == 192 && cg == 2)),
                "launch_gemm: bad config cg=%d bn=%d", cg, bn);
