@@ -80,7 +80,9 @@ class PLIP:
         if getattr(self, "_pin", None) is None or self._pin.shape[0] < cap:
             # tiles that are already 224x224 are decoded straight into ONE reusable pinned buffer (no np.stack, no
             # pageable staging copy): the upload is then a direct DMA inside plip_encode_images_host
-            self._pin = torch.empty((cap, SIZE, SIZE, 3), dtype=torch.uint8).pin_memory()
+            self._pin = torch.empty((cap, SIZE, SIZE, 3), dtype=torch.uint8)
+            if torch.cuda.is_available():
+                self._pin = self._pin.pin_memory()
         pin_np = self._pin.numpy()
         fill = 0                          # tiles waiting in the pinned buffer
         pending: List[np.ndarray] = []   # decoded RGB arrays that still need a resize, any size
