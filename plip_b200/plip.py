@@ -74,33 +74,33 @@ class PLIP:
         if len(images) == 0:
             raise ValueError("need at least one array to stack")  # np.stack([]) in the reference
         eng = self.model.engine
-        cap = eng.max_micro_batch
-        flush_bytes = 1 << 30            # decoded pixels of odd-sized images held on the host per flush
+        flush = max(int(batch_size), eng.max_micro_batch)
+        flush_bytes = 1 << 30            # decoded pixels held on the host (and uploaded at once) per flush
         out = np.empty((len(images), 512), dtype=np.float32)
-        if getattr(self, "_pin", None) is None or self._pin.shape[0] < cap:
-            # tiles that are already 224x224 are decoded straight into ONE reusable pinned buffer (no np.stack, no
-            # pageable staging copy): the upload is then a direct DMA inside plip_encode_images_host
-            self._pin = torch.empty((cap, SIZE, SIZE, 3), dtype=torch.uint8)
-            if torch.cuda.is_available():
-                self._pin = self._pin.pin_memory()
-        pin_np = self._pin.numpy()
-        fill = 0                          # tiles waiting in the pinned buffer
-        pending: List[np.ndarray] = []   # decoded RGB arrays that still need a resize, any size
+        pending: List[np.ndarray] = []   # decoded RGB arrays, any size
         done = 0
         pbar = tqdm(total=len(images) // batch_size, position=0)
 
-        def _flush_tiles():
-            nonlocal fill, done
-            if fill:
-                out[done:done + fill] = eng.encode_images_host(self._pin[:fill]).numpy()
-                done += fill
-                fill = 0
+        def _tile_buffer(n: int) -> torch.Tensor:
+            # ONE reusable (pinned, when a GPU exists) uint8 buffer for batches of 224x224 tiles: no np.stack
+            # allocation per flush, and the upload inside plip_encode_images_host is a direct DMA (no staging copy)
+            if getattr(self, "_pin", None) is None or self._pin.shape[0] < n:
+                self._pin = torch.empty((max(n, flush), SIZE, SIZE, 3), dtype=torch.uint8)
+                if torch.cuda.is_available():
+                    self._pin = self._pin.pin_memory()
+            return self._pin[:n]
 
-        def _flush_odd():
+        def _flush():
             nonlocal pending, done
             if not pending:
                 return
-            if self.device_resize and all(device_resizable(a.shape[1], a.shape[0]) for a in pending):
+            if all(a.shape == (SIZE, SIZE, 3) for a in pending):
+                buf = _tile_buffer(len(pending))
+                view = buf.numpy()
+                for i, a in enumerate(pending):
+                    view[i] = a
+                res = eng.encode_images_host(buf).numpy()
+            elif self.device_resize and all(device_resizable(a.shape[1], a.shape[0]) for a in pending):
                 # upload the decoded images once; Pillow-exact bicubic resize + centre crop on the device
                 buf, descs = pack_rgb(pending, crop="floor", pinned=True)
                 tiles = eng.resize_crop(buf.to(eng.device, non_blocking=True), descs)
@@ -112,23 +112,11 @@ class PLIP:
             pending = []
 
         for chunk in chunks(images, int(batch_size)):
-            for arr in decode_rgb(chunk, self.num_workers):
-                if arr.shape == (SIZE, SIZE, 3):
-                    if pending:                   # keep the caller's order: odd-sized images before this tile go first
-                        _flush_odd()
-                    pin_np[fill] = arr
-                    fill += 1
-                    if fill == cap:
-                        _flush_tiles()
-                else:
-                    if fill:
-                        _flush_tiles()
-                    pending.append(arr)
-                    if len(pending) >= cap or sum(a.nbytes for a in pending) >= flush_bytes:
-                        _flush_odd()
+            pending.extend(decode_rgb(chunk, self.num_workers))
+            if len(pending) >= flush or sum(a.nbytes for a in pending) >= flush_bytes:
+                _flush()
             pbar.update(1)
-        _flush_tiles()
-        _flush_odd()
+        _flush()
         pbar.close()
         return out
 
