@@ -131,11 +131,8 @@ __device__ __forceinline__ void rpf_issue(const float* x, int ldo, int M, uint32
 // LN_FOLD: rstd * acc + (bias' - (rstd * mean) * colsum)  ==  rstd * (acc - mean * colsum) + bias'; the warp's colsum
 // slice is stored Cfg::VEC_FLOATS floats after its bias slice.  `nrm` = -rstd * mean.
 template <bool HAS_BIAS, bool LN_FOLD, int BN>
-__device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, float nrm, float rstd,
+__device__ __forceinline__ void acc_math32(const uint32_t (&v)[32], uint32_t bias_smem, float nrm, float rstd,
                                            float2 (&f)[16]) {
-  uint32_t v[32];
-  tmem_ld32(taddr, v);
-  tmem_ld_wait();
   const float2 nrm2 = make_float2(nrm, nrm), rstd2 = make_float2(rstd, rstd);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -155,6 +152,14 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, f
       f[2 * i + 1] = a1;
     }
   }
+}
+template <bool HAS_BIAS, bool LN_FOLD, int BN>
+__device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, float nrm, float rstd,
+                                           float2 (&f)[16]) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+  tmem_ld_wait();
+  acc_math32<HAS_BIAS, LN_FOLD, BN>(v, bias_smem, nrm, rstd, f);
 }
 
 // One accumulator tile (this warp's 32 rows x BN columns) -> global memory.
@@ -192,28 +197,39 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
       // 64 columns -> 128 B of bf16 per row.  The math runs BEFORE the wait for the previous bulk store of this
       // warp's staging block, so the store's smem read (and the TMEM load) overlap instead of serialising.
       uint32_t pk[32];
-      bool skip = false;
-#pragma unroll
-      for (int half2 = 0; half2 < 2; ++half2) {
-        float2 f[16];
-        load_acc32<HAS_BIAS, LN_FOLD, BN>(tmem_row_base + blk * 64 + half2 * 32, bias_smem + ((blk >> 1) * 64 + half2 * 32) * 4,
-                                          mean, rstd, f);
+      {
+        // both 32-column halves of the block are loaded from TMEM before the single wait, and their math is
+        // independent: two TMEM latencies and two dependency chains overlap instead of running back to back
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem_row_base + blk * 64, v0);
+#ifdef PLIP_EPI_SERIAL_LD   // A/B build switch (tools/r2_call10.sh): the round-1 order, one wait per half
+        tmem_ld_wait();
+#endif
+        tmem_ld32(tmem_row_base + blk * 64 + 32, v1);
+        tmem_ld_wait();
+        float2 f0[16], f1[16];
+        acc_math32<HAS_BIAS, LN_FOLD, BN>(v0, bias_smem + ((blk >> 1) * 64) * 4, mean, rstd, f0);
+        acc_math32<HAS_BIAS, LN_FOLD, BN>(v1, bias_smem + ((blk >> 1) * 64 + 32) * 4, mean, rstd, f1);
         if (p.dbg >= 2) {
           float a = 0.f;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) a += f[i].x + f[i].y;
+          for (int i = 0; i < 16; ++i) a += (f0[i].x + f0[i].y) + (f1[i].x + f1[i].y);
           if (a == 1.2345e30f) reinterpret_cast<float*>(p.out)[0] = a;
-          skip = true;
           continue;
         }
         if constexpr (GELU) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = quick_gelu2(f[i]);
+          for (int i = 0; i < 16; ++i) {
+            f0[i] = quick_gelu2(f0[i]);
+            f1[i] = quick_gelu2(f1[i]);
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[half2 * 16 + i] = pack_op2<F16>(f[i].x, f[i].y);
+        for (int i = 0; i < 16; ++i) {
+          pk[i] = pack_op2<F16>(f0[i].x, f0[i].y);
+          pk[16 + i] = pack_op2<F16>(f1[i].x, f1[i].y);
+        }
       }
-      if (skip) continue;
       if (p.tma_store) {  // the previous bulk store must have finished reading this staging block
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
