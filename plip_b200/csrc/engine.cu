@@ -547,6 +547,15 @@ bool graph_eligible(const plip_engine* e, int64_t n) {
   return e->graph_max_n > 0 && n <= e->graph_max_n && n <= e->max_mb && !e->prof_on;
 }
 
+// A caller that cycles through many batch sizes / formats must not accumulate executable graphs without bound.
+constexpr size_t kMaxGraphs = 96;
+void trim_graphs(plip_engine* e) {
+  if (e->graphs.size() < kMaxGraphs) return;
+  cudaDeviceSynchronize();  // none of them may still be running
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  e->graphs.clear();
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -735,6 +744,7 @@ PLIP_API int plip_encode_images(plip_engine_t* e, const void* pixels_dev, int pi
       if (int rc = vision_forward(e, pixels_dev, pixel_format, n, out_dev, normalize, st)) return rc;
       cudaGraphExec_t ge = nullptr;
       if (int rc = capture_graph(e, [&](cudaStream_t cs) { return vision_forward(e, e->g_in, pixel_format, n, e->g_out, normalize, cs); }, &ge)) return rc;
+      trim_graphs(e);
       e->graphs.emplace(key, ge);
     } else {
       PLIP_CUDA_CHECK(cudaMemcpyAsync(e->g_in, pixels_dev, (size_t)n * pb, cudaMemcpyDeviceToDevice, st));
@@ -790,6 +800,7 @@ PLIP_API int plip_encode_text_prefix(plip_engine_t* e, const void* ids_dev, int 
             return text_forward(e, e->g_in, ids_dtype, attention_mask_dev ? e->g_mask : nullptr, n, prefix_len, seq_len,
                                 e->g_out, normalize, cs);
           }, &ge)) return rc;
+      trim_graphs(e);
       e->graphs.emplace(key, ge);
     } else {
       PLIP_CUDA_CHECK(cudaMemcpyAsync(e->g_in, ids_dev, ib, cudaMemcpyDeviceToDevice, st));
