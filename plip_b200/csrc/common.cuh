@@ -234,6 +234,18 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtenso
       : "memory");
 }
 
+// Same, multicast: the tile lands at the same shared-memory offset of every CTA in `cta_mask` (cluster ranks), and the
+// completion bytes are credited, for each destination CTA, to the barrier at `bar_cluster_addr`'s offset in that
+// destination's pair (the even CTA when `bar_cluster_addr` names an even CTA: the pair leaders in a 2-SM pipeline).
+__device__ __forceinline__ void tma_load_2d_cg2_mc(uint32_t smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr,
+                                                   int32_t c0, int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
 // 2-D tile store smem -> global (bulk async group); rows / columns outside the tensor are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -377,6 +389,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
         "h"(mask)
         : "memory");
   }
+}
+
+// cta_group::2 commit with an explicit cluster-rank mask (clusters of more than one CTA pair)
+__device__ __forceinline__ void umma_commit_mask(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
 }
 
 // ---------------------------------------------------------------------------

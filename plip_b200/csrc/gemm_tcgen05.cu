@@ -370,10 +370,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
   }
 }
 
-template <int CG, int BN, int EPI, bool F16>
+// QUAD (experimental, PLIP_GEMM_QUAD=1): a cluster of TWO CTA pairs works on neighbouring M blocks of the same N block
+// and takes the W tile with ONE multicast TMA load per half (pair 0 loads, both pairs receive) — 25 % fewer operand
+// bytes through L2, the resource every layer GEMM is bound by (profiles/r2_notes.md §6).  Pair 0's stage slots are
+// released by the MMA commits of BOTH pairs; everything else (accumulator barriers, TMEM, epilogue) stays per pair.
+template <int CG, int BN, int EPI, bool F16, bool QUAD = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
+  static_assert(!QUAD || CG == 2, "the two-pair cluster is built from CTA pairs");
+  constexpr int CL = QUAD ? 4 : CG;  // CTAs per cluster
   using C = Cfg<CG, BN, EPI>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -395,7 +401,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;  // rank inside the cluster
+  const uint32_t cta_rank = crank & (CG - 1);                  // rank inside the CTA pair
+  const uint32_t pair = QUAD ? (crank >> 1) : 0u;              // which pair of the cluster
+  const uint32_t lead_rank = crank & ~1u;                       // cluster rank of this pair's leader
   const bool leader = (cta_rank == 0);
 
   if (warp == kWarpTma && lane == 0) {
@@ -405,7 +414,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == kWarpMma && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), CG);  // leader's arrive.expect_tx (+ peer's remote arrive)
-      mbar_init(empty_bar(s), 1);  // tcgen05.commit
+      mbar_init(empty_bar(s), (QUAD && pair == 0) ? 2 : 1);  // tcgen05.commit (QUAD: of both pairs for the W multicaster)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);        // tcgen05.commit
@@ -415,17 +424,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == kWarpTmem) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base =
       *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
 
   const int num_n_blk = p.N / BN;
   const int num_m_blk = (p.M + BM * CG - 1) / (BM * CG);
-  const int num_tiles = num_m_blk * num_n_blk;
+  // QUAD: a work item is a pair of neighbouring M blocks x one N block; an odd M-block count leaves the second pair of the
+  // last item with rows past M only (zero-filled loads, nothing stored)
+  const int num_tiles = (QUAD ? (num_m_blk + 1) / 2 : num_m_blk) * num_n_blk;
   const int num_kb = p.K / BK;
-  const int tile0 = blockIdx.x / CG;
-  const int tile_step = gridDim.x / CG;
+  const int tile0 = blockIdx.x / CL;
+  const int tile_step = gridDim.x / CL;
+  auto m_block_of = [&](int t) { const int mb = t / num_n_blk; return QUAD ? 2 * mb + (int)pair : mb; };
 
   if (warp == kWarpTma) {
     // ===================== TMA producer =====================
@@ -433,7 +445,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int s = 0;
       uint32_t ph = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
-        const int m_blk = t / num_n_blk, n_blk = t - m_blk * num_n_blk;
+        const int m_blk = m_block_of(t), n_blk = t % num_n_blk;
         const int m0 = m_blk * BM * CG + cta_rank * BM;
         const int n0 = n_blk * BN + cta_rank * C::LOAD_N;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -445,11 +457,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d(sa, &tmA, full_bar(s), kb * BK, m0);
             tma_load_2d(sb, &tmB, full_bar(s), kb * BK, n0);
           } else {
-            const uint32_t lfull = mapa_shared(full_bar(s), 0);
+            const uint32_t lfull = mapa_shared(full_bar(s), lead_rank);
             if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C::STAGE);
             else mbar_arrive_cluster(lfull);
             tma_load_2d_cg2(sa, &tmA, lfull, kb * BK, m0);
-            tma_load_2d_cg2(sb, &tmB, lfull, kb * BK, n0);
+            if constexpr (!QUAD) {
+              tma_load_2d_cg2(sb, &tmB, lfull, kb * BK, n0);
+            } else if (pair == 0) {
+              // this CTA's half of the W tile, delivered to the same slot of CTA cta_rank of BOTH pairs
+              // (barrier operand: this CTA's own offset with the pair's peer bit cleared = "the even CTA of the pair",
+              // which the hardware resolves per destination CTA — the addressing CUTLASS' 2-SM multicast atoms use)
+              tma_load_2d_cg2_mc(sb, &tmB, full_bar(s) & 0xFEFFFFFFu, kb * BK, n0,
+                                 static_cast<uint16_t>((1u << cta_rank) | (1u << (cta_rank + 2))));
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -461,6 +481,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr uint32_t idesc = make_idesc_op(BM * CG, BN, 0, 0, F16);
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
+      // commit targets: the stage barriers of this pair — plus, for the second pair of a QUAD cluster, those of the first
+      // pair, whose producers refill the shared W slot — and the accumulator barrier of this pair
+      const uint16_t empty_mask = QUAD ? (pair == 0 ? 0x3 : 0xF) : 0x3;
+      const uint16_t tfull_mask = QUAD ? static_cast<uint16_t>(0x3u << (2 * pair)) : 0x3;
       for (int t = tile0; t < num_tiles; t += tile_step) {
         mbar_wait(tempty_bar(a), aph ^ 1u);
         tc_fence_after();
@@ -474,10 +498,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_ss<CG>(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit<CG>(empty_bar(s));
+          if constexpr (CG == 2) umma_commit_mask(empty_bar(s), empty_mask); else umma_commit<CG>(empty_bar(s));
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        umma_commit<CG>(tfull_bar(a));
+        if constexpr (CG == 2) umma_commit_mask(tfull_bar(a), tfull_mask); else umma_commit<CG>(tfull_bar(a));
         a ^= 1;
         if (a == 0) aph ^= 1u;
       }
@@ -492,7 +516,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int a = 0;
     uint32_t aph = 0;
     for (int t = tile0; t < num_tiles; t += tile_step) {
-      const int m_blk = t / num_n_blk, n_blk = t - m_blk * num_n_blk;
+      const int m_blk = m_block_of(t), n_blk = t % num_n_blk;
       if constexpr (HAS_BIAS) {
         // this warp's slice of the bias (and colsum) vector: the (about BN / 2) columns it will touch, in its own order
         // (column blocks half, half + 2, ... of W columns).  Private to the warp: __syncwarp instead of a 256-thread
@@ -561,7 +585,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) {
         if constexpr (CG == 1) mbar_arrive(tempty_bar(a));
-        else mbar_arrive_cluster(mapa_shared(tempty_bar(a), 0));
+        else mbar_arrive_cluster(mapa_shared(tempty_bar(a), lead_rank));
       }
       a ^= 1;
       if (a == 0) aph ^= 1u;
@@ -570,7 +594,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all(); else __syncthreads();
   if (warp == kWarpTmem) tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
 }
 
@@ -590,17 +614,18 @@ int num_sms() {
   return n;
 }
 
-template <int CG, int BN, int EPI, bool F16>
+template <int CG, int BN, int EPI, bool F16, bool QUAD = false>
 int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   using C = Cfg<CG, BN, EPI>;
-  auto kern = gemm_kernel<CG, BN, EPI, F16>;
+  constexpr int CL = QUAD ? 4 : CG;  // CTAs per cluster
+  auto kern = gemm_kernel<CG, BN, EPI, F16, QUAD>;
   static unsigned long long configured = 0;
-  static int max_groups = 0;  // co-resident CTAs (CG == 1) or CTA pairs (CG == 2) for this kernel
+  static int max_groups = 0;  // co-resident clusters (CTAs for CG == 1, CTA pairs for CG == 2, two pairs for QUAD)
   if (first_use_on_device(configured)) {
     PLIP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM_BYTES));
-    max_groups = num_sms() / CG;
-    if (CG == 2) {
+    max_groups = num_sms() / CL;
+    if (CL >= 2) {
       // A persistent grid must be fully co-resident: ask how many CTA pairs fit at once (SM pairs
       // must share a TPC, so this can be below num_sms / 2).
       cudaLaunchConfig_t q = {};
@@ -609,7 +634,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
       q.dynamicSmemBytes = C::SMEM_BYTES;
       cudaLaunchAttribute qa[1];
       qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = CG; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
       q.attrs = qa; q.numAttrs = 1;
       int n_clusters = 0;
       PLIP_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q));
@@ -618,7 +643,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
     const int env_groups = env_int("PLIP_GEMM_GROUPS", 0);
     if (env_groups > 0) max_groups = env_groups;
     if (env_int("PLIP_DEBUG", 0))
-      fprintf(stderr, "plip_b200: gemm<cg=%d,bn=%d,epi=%d> stages=%d smem=%u max_groups=%d\n", CG, BN, EPI,
+      fprintf(stderr, "plip_b200: gemm<cg=%d,bn=%d,epi=%d,cluster=%d> stages=%d smem=%u max_groups=%d\n", CG, BN, EPI, CL,
               C::STAGES, C::SMEM_BYTES, max_groups);
   }
   CUtensorMap tmA, tmB;
@@ -642,17 +667,30 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   p.xb_out = g.xb_out; p.stats_out = g.stats_out;
   if (g.n_tiles_used) *g.n_tiles_used = 2 * (g.N / BN);
 
-  const int num_tiles = ((g.M + BM * CG - 1) / (BM * CG)) * (g.N / BN);
+  const int num_m_blk = (g.M + BM * CG - 1) / (BM * CG);
+  const int num_tiles = (QUAD ? (num_m_blk + 1) / 2 : num_m_blk) * (g.N / BN);
   int groups = max_groups;
   if (groups > num_tiles) groups = num_tiles;
 
-  PLIP_CUDA_CHECK(launch_kernel(kern, dim3(groups * CG), dim3(kThreads), C::SMEM_BYTES, stream, CG, tmA, tmB, tmC, p));
+  PLIP_CUDA_CHECK(launch_kernel(kern, dim3(groups * CL), dim3(kThreads), C::SMEM_BYTES, stream, CL, tmA, tmB, tmC, p));
   ++g_launch_count;
   return 0;
 }
 
 template <int CG, int BN, bool F16>
 int launch_epi_fmt(const GemmArgs& g, cudaStream_t stream) {
+  if constexpr (CG == 2) {
+    // experimental two-pair clusters with a multicast W tile: the three layer epilogues only, opt-in
+    static const int env_quad = env_int("PLIP_GEMM_QUAD", 0);
+    if (env_quad && !g.force_cg) {
+      switch (g.epi) {
+        case EPI_BIAS_RESID_F32: return launch_inst<2, BN, EPI_BIAS_RESID_F32, F16, true>(g, stream);
+        case EPI_LN_BIAS_BF16: return launch_inst<2, BN, EPI_LN_BIAS_BF16, F16, true>(g, stream);
+        case EPI_LN_BIAS_GELU_BF16: return launch_inst<2, BN, EPI_LN_BIAS_GELU_BF16, F16, true>(g, stream);
+        default: break;
+      }
+    }
+  }
   switch (g.epi) {
     case EPI_BIAS_BF16: return launch_inst<CG, BN, EPI_BIAS_BF16, F16>(g, stream);
     case EPI_BIAS_GELU_BF16: return launch_inst<CG, BN, EPI_BIAS_GELU_BF16, F16>(g, stream);
