@@ -608,6 +608,19 @@ def bench_pairs(ctx):
                                "frac_of_sustained_peak": PAIRS * FLOP_TXT / ms_t / 1e9 / peaks["bf16_tflops_sustained"]},
     }
     extra["step_frac_of_sustained_peak"] = extra["step_tflops"] / peaks["bf16_tflops_sustained"]
+    if ws == 1:
+        # opt-in engine option, NOT the headline: the last layer's out_proj / LN2 / MLP on the pooled rows only
+        # (identical embeddings, tests/test_gpu_model.py::test_last_layer_pruning_gives_the_same_embeddings)
+        eng.set_last_layer_pruning(True)
+        try:
+            for i in range(3):
+                step(i)
+            ms_p = timer.timed(step, args.steps)
+        finally:
+            eng.set_last_layer_pruning(False)
+        extra["last_layer_pruning_opt_in"] = {"value": PAIRS * args.steps / (ms_p / 1e3), "unit": "pairs/s",
+                                              "ms_per_step": ms_p / args.steps,
+                                              "what": "same step with Engine.set_last_layer_pruning(True); `value` above is measured without it"}
     if not args.quick:
         extra["kernels_alone_burst"] = kernel_bursts(eng, peaks, torch.cuda.current_stream().cuda_stream)
         extra.update(product_api_extras(ctx, tower))

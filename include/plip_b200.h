@@ -32,7 +32,7 @@ extern "C" {
 
 #define PLIP_API __attribute__((visibility("default")))
 
-#define PLIP_B200_ABI_VERSION 4  /* 3: + plip_resize_crop_u8; 4: + plip_profile_*, plip_create_ex (operand format) */
+#define PLIP_B200_ABI_VERSION 5  /* 3: + plip_resize_crop_u8; 4: + plip_profile_*, plip_create_ex (operand format); 5: + plip_set_last_layer_pruning */
 
 /* Model constants (TF:configuration_clip.py:47-64,97-109,160-161). */
 #define PLIP_IMAGE_SIZE 224
@@ -109,6 +109,13 @@ PLIP_API int plip_operand_format(const plip_engine_t* e);
  * largest id, as legacy configs (eos_token_id == 2 — what openai/clip-vit-base-patch32 ships) and OpenAI clip's
  * text.argmax(-1) do (TF:564-570).  Captions that contain an eos are pooled at its first position either way. */
 PLIP_API int plip_set_text_pooling(plip_engine_t* e, int no_eos_argmax);
+/* Last-layer pruning for the embedding calls (default 0 = off).  Only the pooled row of a sequence leaves a tower
+ * (CLS: TF:685-686; first eos: TF:571-584), and after the last layer's attention rows no longer interact, so with
+ * on != 0 plip_encode_* / plip_clip_forward* run that layer's out_proj, LayerNorm 2 and MLP on the n pooled rows
+ * instead of all n*seq rows: the embeddings are the same (same per-row arithmetic), the step is ~5 % shorter at
+ * batch 1024 and more for small batches.  plip_hidden_states is never pruned.  plip_last_layer_pruning reads it back. */
+PLIP_API int plip_set_last_layer_pruning(plip_engine_t* e, int on);
+PLIP_API int plip_last_layer_pruning(const plip_engine_t* e);
 
 /* ---- the hot path -------------------------------------------------------------------------- */
 /* Vision tower + visual_projection: replaces CLIPModel.get_image_features (TF:829-863, called at

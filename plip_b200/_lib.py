@@ -66,6 +66,8 @@ SIGNATURES = {
     "plip_create_ex": (_i, [_vp, _u64, _f, _i, _i, _i, C.POINTER(_vp)]),
     "plip_operand_format": (_i, [_vp]),
     "plip_set_text_pooling": (_i, [_vp, _i]),
+    "plip_set_last_layer_pruning": (_i, [_vp, _i]),
+    "plip_last_layer_pruning": (_i, [_vp]),
     "plip_dbg_set_operand_format": (_i, [_i]),
     "plip_destroy": (_i, [_vp]),
     "plip_workspace_bytes": (_u64, [_i]),

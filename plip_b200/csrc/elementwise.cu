@@ -273,6 +273,24 @@ __global__ void __launch_bounds__(kEwThreads) cls_rows_kernel(const float* __res
   }
 }
 
+// Pooled-row gather for the pruned last layer (engine.cu run_layers): copies row idx(i) of the 16-bit attention
+// output and of the fp32 residual stream into compact [n, dim] buffers.  idx(i) = row_index[i], or i * row_stride
+// when row_index is null (the vision CLS rows).  16-byte pieces, one per thread.
+__global__ void __launch_bounds__(kEwThreads) gather_rows_kernel(const uint4* __restrict__ a16, const uint4* __restrict__ x32,
+                                                                 const int32_t* __restrict__ row_index, int64_t row_stride,
+                                                                 int64_t n, int dim, uint4* __restrict__ a16_out,
+                                                                 uint4* __restrict__ x32_out) {
+  const int v16 = dim / 8, v32 = dim / 4, per_row = v16 + v32;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * per_row;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / per_row;
+    const int j = (int)(i % per_row);
+    const int64_t src = row_index ? (int64_t)row_index[r] : r * row_stride;
+    if (j < v16) a16_out[r * v16 + j] = a16[src * v16 + j];
+    else x32_out[r * v32 + (j - v16)] = x32[src * v32 + (j - v16)];
+  }
+}
+
 // x[r] /= sqrt(sum x[r]^2): _get_vector_norm, no epsilon (TF:57-65,923-924). One warp per row.
 __global__ void __launch_bounds__(kEwThreads) l2_normalize_kernel(float* __restrict__ x, int64_t rows,
                                                                   int dim) {
@@ -384,6 +402,18 @@ int launch_mask_to_i32(const void* mask, int dtype, int64_t count, int seq_len, 
 
 int launch_cls_rows(const float* cls, const float* pos, int64_t n, float* x, cudaStream_t st) {
   PLIP_CUDA_CHECK(launch_kernel(cls_rows_kernel, dim3(grid_for(n * (kVisDim / 4), kEwThreads)), dim3(kEwThreads), 0, st, 1, cls, pos, n, x));
+  PLIP_CUDA_CHECK(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+int launch_gather_rows(const __nv_bfloat16* a16, const float* x32, const int32_t* row_index, int64_t row_stride,
+                       int64_t n, int dim, __nv_bfloat16* a16_out, float* x32_out, cudaStream_t st) {
+  PLIP_REQUIRE(n > 0 && dim > 0 && dim % 8 == 0, "gather_rows: bad shape");
+  const int64_t items = n * (dim / 8 + dim / 4);
+  PLIP_CUDA_CHECK(launch_kernel(gather_rows_kernel, dim3(grid_for(items, kEwThreads)), dim3(kEwThreads), 0, st, 1,
+                                reinterpret_cast<const uint4*>(a16), reinterpret_cast<const uint4*>(x32), row_index,
+                                row_stride, n, dim, reinterpret_cast<uint4*>(a16_out), reinterpret_cast<uint4*>(x32_out)));
   PLIP_CUDA_CHECK(cudaGetLastError());
   ++g_launch_count;
   return 0;

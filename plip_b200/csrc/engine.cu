@@ -125,6 +125,7 @@ struct plip_engine {
   int device = 0;
   int max_mb = 0;
   int text_pool_argmax = 0;  // rows without an eos token: 0 = position 0 (HF, eos_token_id 49407), 1 = argmax of the ids (legacy / OpenAI)
+  int prune_last = 0;  // plip_set_last_layer_pruning: embedding calls run the last layer's out_proj / MLP on the pooled rows only
   int f16 = 0;  // 16-bit operand format of the packed GEMM weights and of every activation operand: 0 bf16, 1 IEEE half
   float logit_scale_exp = 1.f;
   uint8_t* d_blob = nullptr;
@@ -146,6 +147,7 @@ struct plip_engine {
   __nv_bfloat16* pooled = nullptr;  // [mb, 768]
   int32_t* row_idx = nullptr;       // [mb] EOS rows
   int32_t* kmask = nullptr;         // [mb*77] key padding mask
+  const float* pooled_x = nullptr;  // set by run_layers when the last layer was pruned: compact fp32 [n_seq, D] pooled rows
   // last use of the shared workspace through the device-pointer API (any caller stream): the host-buffer
   // path, which runs on the engine's own streams, waits for it before touching the workspace
   cudaEvent_t ev_last = nullptr;
@@ -262,8 +264,16 @@ WsLayout ws_layout(int mb) {
 
 // Encoder layers with both LayerNorms folded into the consuming GEMMs.  On entry X holds the residual
 // stream; Xn / stats are (re)derived from it here and afterwards maintained by the residual epilogues.
+//
+// prune (embedding calls with plip_set_last_layer_pruning on; never for hidden-state requests): only the pooled row of
+// each sequence leaves the tower (CLS, TF:modeling_clip.py:685; first-EOS row, :571-584), and after the last layer's
+// attention nothing mixes rows any more, so that layer's out_proj, LN2, fc1 and fc2 are run on the n_seq pooled rows
+// alone (gathered into compact buffers) instead of all n_seq*S rows — same arithmetic per row, identical embeddings.
+// pool_idx: device row indices of the pooled rows (null = row i*S).  On return e->pooled_x points at them.
 int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int FF, int heads, bool causal,
-               const int32_t* kmask, int num_layers, cudaStream_t st) {
+               const int32_t* kmask, int num_layers, cudaStream_t st, bool prune = false,
+               const int32_t* pool_idx = nullptr) {
+  e->pooled_x = nullptr;
   const int64_t M = n_seq * S;
   PLIP_REQUIRE(M <= 0x7fffffff / 4, "micro-batch too large");
   if (num_layers <= 0) return 0;
@@ -295,6 +305,44 @@ int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int
     {
       ProfScope ps(e, st, PK_ATTN, f_att, b_att);
       if (int rc = launch_attention(e->QKV, n_seq, S, heads, causal, kmask, e->AO, e->f16, st)) return rc;
+    }
+    if (prune && l + 1 == num_layers) {
+      // compact copies of the pooled rows: attention output -> head of the (now free) QKV buffer, residual rows behind it
+      const double dn = (double)n_seq;
+      __nv_bfloat16* ao_p = e->QKV;
+      float* x_p = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(e->QKV) + (((size_t)n_seq * D * 2 + 1023) & ~(size_t)1023));
+      {
+        ProfScope ps(e, st, PK_MISC, 0, dn * dD * 12);
+        if (int rc = launch_gather_rows(e->AO, e->X, pool_idx, S, n_seq, D, ao_p, x_p, st)) return rc;
+      }
+      g = GemmArgs();
+      g.f16 = e->f16;
+      g.A = ao_p; g.lda = D; g.W = w.wo; g.ldw = D; g.M = (int)n_seq; g.N = D; g.K = D;
+      g.bias = w.bo; g.out = x_p; g.ldo = D; g.epi = EPI_BIAS_RESID_F32;
+      g.xb_out = e->Xn; g.stats_out = e->stats; g.n_tiles_used = &np;
+      {
+        ProfScope ps(e, st, PK_OUT, 2.0 * dn * dD * dD, dn * dD * 12 + dD * dD * 2);
+        if (int rc = launch_gemm(g, st)) return rc;
+      }
+      g = GemmArgs();
+      g.f16 = e->f16;
+      g.A = e->Xn; g.lda = D; g.W = w.w1; g.ldw = D; g.M = (int)n_seq; g.N = FF; g.K = D;
+      g.bias = w.b1; g.colsum = w.s1; g.stats_in = e->stats; g.n_partials = np;
+      g.out = e->H; g.ldo = FF; g.epi = EPI_LN_BIAS_GELU_BF16;
+      {
+        ProfScope ps(e, st, PK_FC1, 2.0 * dn * dD * dF, dn * dD * 2 + dD * dF * 2 + dn * dF * 2);
+        if (int rc = launch_gemm(g, st)) return rc;
+      }
+      g = GemmArgs();
+      g.f16 = e->f16;
+      g.A = e->H; g.lda = FF; g.W = w.w2; g.ldw = FF; g.M = (int)n_seq; g.N = D; g.K = FF;
+      g.bias = w.b2; g.out = x_p; g.ldo = D; g.epi = EPI_BIAS_RESID_F32;
+      {
+        ProfScope ps(e, st, PK_FC2, 2.0 * dn * dD * dF, dn * dF * 2 + dD * dF * 2 + dn * dD * 8);
+        if (int rc = launch_gemm(g, st)) return rc;
+      }
+      e->pooled_x = x_p;
+      break;
     }
     g = GemmArgs();
     g.f16 = e->f16;
@@ -331,7 +379,8 @@ int run_layers(plip_engine* e, const LayerW* L, int64_t n_seq, int S, int D, int
 }
 
 // Vision tower up to (and including) `num_layers` encoder layers; X holds the residual stream.
-int vision_trunk(plip_engine* e, const void* pixels, int fmt, int64_t mb, int num_layers, cudaStream_t st) {
+int vision_trunk(plip_engine* e, const void* pixels, int fmt, int64_t mb, int num_layers, cudaStream_t st,
+                 bool prune = false) {
   e->prof_tower = 0;
   const double dmb = (double)mb;
   {
@@ -357,17 +406,18 @@ int vision_trunk(plip_engine* e, const void* pixels, int fmt, int64_t mb, int nu
     ProfScope ps(e, st, PK_LN, 0, (double)M * kVisDim * 8);
     if (int rc = launch_layernorm(e->X, nullptr, kVisDim, M, kVisDim, e->v_pre_g, e->v_pre_b, e->X, nullptr, e->f16, st)) return rc;
   }
-  return run_layers(e, e->vis, mb, kVisSeq, kVisDim, kVisFF, kVisHeads, false, nullptr, num_layers, st);
+  return run_layers(e, e->vis, mb, kVisSeq, kVisDim, kVisFF, kVisHeads, false, nullptr, num_layers, st, prune, nullptr);
 }
 
 int vision_forward(plip_engine* e, const void* pixels, int fmt, int64_t mb, float* out, int normalize,
                    cudaStream_t st) {
-  if (int rc = vision_trunk(e, pixels, fmt, mb, kLayers, st)) return rc;
+  if (int rc = vision_trunk(e, pixels, fmt, mb, kLayers, st, e->prune_last != 0)) return rc;
   // pooled = post_layernorm(last_hidden_state[:, 0, :])                  TF:modeling_clip.py:685-686
   {
     ProfScope ps(e, st, PK_LN, 0, (double)mb * kVisDim * 6);
-    if (int rc = launch_layernorm(e->X, nullptr, (int64_t)kVisSeq * kVisDim, mb, kVisDim, e->v_post_g, e->v_post_b,
-                                  nullptr, e->pooled, e->f16, st)) return rc;
+    const float* src = e->pooled_x ? e->pooled_x : e->X;  // compact CLS rows when the last layer was pruned
+    if (int rc = launch_layernorm(src, nullptr, e->pooled_x ? (int64_t)kVisDim : (int64_t)kVisSeq * kVisDim, mb, kVisDim,
+                                  e->v_post_g, e->v_post_b, nullptr, e->pooled, e->f16, st)) return rc;
   }
   GemmArgs g;
   g.f16 = e->f16;
@@ -388,7 +438,7 @@ int vision_forward(plip_engine* e, const void* pixels, int fmt, int64_t mb, floa
 // Causality makes rows after a caption's first EOS irrelevant to its pooled output (TF:571-584), so callers
 // that know the longest caption of the batch may pass a shorter S: same result, proportionally less work.
 int text_trunk(plip_engine* e, const void* ids, int ids_dtype, const void* mask, int64_t mb, int S, int stride,
-               int num_layers, cudaStream_t st) {
+               int num_layers, cudaStream_t st, bool prune = false) {
   e->prof_tower = 1;
   {
     ProfScope ps(e, st, PK_EMBED, 0, (double)mb * S * kTxtDim * 8);
@@ -400,17 +450,18 @@ int text_trunk(plip_engine* e, const void* ids, int ids_dtype, const void* mask,
     if (int rc = launch_mask_to_i32(mask, ids_dtype, mb * S, S, stride, e->kmask, st)) return rc;
     km = e->kmask;
   }
-  return run_layers(e, e->txt, mb, S, kTxtDim, kTxtFF, kTxtHeads, true, km, num_layers, st);
+  return run_layers(e, e->txt, mb, S, kTxtDim, kTxtFF, kTxtHeads, true, km, num_layers, st, prune, e->row_idx);
 }
 
 int text_forward(plip_engine* e, const void* ids, int ids_dtype, const void* mask, int64_t mb, int S, int stride,
                  float* out, int normalize, cudaStream_t st) {
-  if (int rc = text_trunk(e, ids, ids_dtype, mask, mb, S, stride, kLayers, st)) return rc;
+  if (int rc = text_trunk(e, ids, ids_dtype, mask, mb, S, stride, kLayers, st, e->prune_last != 0)) return rc;
   // pooled = final_layer_norm(last_hidden_state)[b, first eos]            TF:modeling_clip.py:562-584
   {
     ProfScope ps(e, st, PK_LN, 0, (double)mb * kTxtDim * 6);
-    if (int rc = launch_layernorm(e->X, e->row_idx, kTxtDim, mb, kTxtDim, e->t_fin_g, e->t_fin_b, nullptr,
-                                  e->pooled, e->f16, st)) return rc;
+    const float* src = e->pooled_x ? e->pooled_x : e->X;  // compact EOS rows when the last layer was pruned
+    if (int rc = launch_layernorm(src, e->pooled_x ? nullptr : e->row_idx, kTxtDim, mb, kTxtDim, e->t_fin_g, e->t_fin_b,
+                                  nullptr, e->pooled, e->f16, st)) return rc;
   }
   GemmArgs g;
   g.f16 = e->f16;
@@ -726,6 +777,13 @@ PLIP_API int plip_set_text_pooling(plip_engine_t* e, int no_eos_argmax) {
   return 0;
 }
 
+PLIP_API int plip_set_last_layer_pruning(plip_engine_t* e, int on) {
+  PLIP_REQUIRE(e != nullptr, "plip_set_last_layer_pruning: null engine");
+  e->prune_last = on != 0;
+  return 0;
+}
+PLIP_API int plip_last_layer_pruning(const plip_engine_t* e) { return e ? e->prune_last : -1; }
+
 PLIP_API int plip_encode_images(plip_engine_t* e, const void* pixels_dev, int pixel_format, int64_t n,
                                 float* out_dev, int normalize, void* stream) {
   PLIP_REQUIRE(e && pixels_dev && out_dev, "plip_encode_images: null argument");
@@ -735,7 +793,7 @@ PLIP_API int plip_encode_images(plip_engine_t* e, const void* pixels_dev, int pi
   PLIP_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_last, 0));  // calls on different streams share one workspace
   const size_t pb = pixel_bytes(pixel_format);
   if (graph_eligible(e, n)) {
-    const auto key = std::make_tuple(0, (int)n, pixel_format, normalize ? 1 : 0, 0, 0, 0);
+    const auto key = std::make_tuple(0 + 4 * e->prune_last, (int)n, pixel_format, normalize ? 1 : 0, 0, 0, 0);
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
       // first call of this shape: run it eagerly (this also configures every kernel), then record the graph
@@ -750,7 +808,7 @@ PLIP_API int plip_encode_images(plip_engine_t* e, const void* pixels_dev, int pi
       PLIP_CUDA_CHECK(cudaMemcpyAsync(e->g_in, pixels_dev, (size_t)n * pb, cudaMemcpyDeviceToDevice, st));
       PLIP_CUDA_CHECK(cudaGraphLaunch(it->second, st));
       PLIP_CUDA_CHECK(cudaMemcpyAsync(out_dev, e->g_out, (size_t)n * kProj * 4, cudaMemcpyDeviceToDevice, st));
-      g_launch_count += 67;
+      g_launch_count += 67 + e->prune_last;
     }
     PLIP_CUDA_CHECK(cudaEventRecord(e->ev_last, st));
     return 0;
@@ -786,7 +844,7 @@ PLIP_API int plip_encode_text_prefix(plip_engine_t* e, const void* ids_dev, int 
   const size_t isz = ids_dtype == PLIP_IDS_I64 ? 8 : 4;
   if (graph_eligible(e, n)) {
     // everything a captured launch sequence bakes in is part of the key (incl. the pooling convention)
-    const auto key = std::make_tuple(1 + 2 * e->text_pool_argmax, (int)n, ids_dtype, normalize ? 1 : 0, seq_len, prefix_len,
+    const auto key = std::make_tuple(1 + 2 * e->text_pool_argmax + 4 * e->prune_last, (int)n, ids_dtype, normalize ? 1 : 0, seq_len, prefix_len,
                                      attention_mask_dev ? 1 : 0);
     const size_t ib = (size_t)n * seq_len * isz;
     auto it = e->graphs.find(key);
@@ -807,7 +865,7 @@ PLIP_API int plip_encode_text_prefix(plip_engine_t* e, const void* ids_dev, int 
       if (attention_mask_dev) PLIP_CUDA_CHECK(cudaMemcpyAsync(e->g_mask, attention_mask_dev, ib, cudaMemcpyDeviceToDevice, st));
       PLIP_CUDA_CHECK(cudaGraphLaunch(it->second, st));
       PLIP_CUDA_CHECK(cudaMemcpyAsync(out_dev, e->g_out, (size_t)n * kProj * 4, cudaMemcpyDeviceToDevice, st));
-      g_launch_count += 66;
+      g_launch_count += 66 + e->prune_last;
     }
     PLIP_CUDA_CHECK(cudaEventRecord(e->ev_last, st));
     return 0;

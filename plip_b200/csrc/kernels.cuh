@@ -19,6 +19,9 @@ int launch_mask_to_i32(const void* mask, int dtype, int64_t count, int seq_len, 
                        cudaStream_t st);
 int launch_cls_rows(const float* cls, const float* pos, int64_t n, float* x, cudaStream_t st);
 int launch_l2_normalize(float* x, int64_t rows, int dim, cudaStream_t st);
+// rows idx(i) (= row_index[i], or i * row_stride) of a 16-bit [*, dim] and an fp32 [*, dim] matrix -> compact [n, dim]
+int launch_gather_rows(const __nv_bfloat16* a16, const float* x32, const int32_t* row_index, int64_t row_stride,
+                       int64_t n, int dim, __nv_bfloat16* a16_out, float* x32_out, cudaStream_t st);
 
 // resize.cu: Pillow-exact bicubic resize + crop of packed RGB uint8 images into [n,224,224,3] tiles.
 int launch_resize_crop(const uint8_t* src, size_t src_bytes, const plip_resize_desc_t* descs_host, int64_t n,

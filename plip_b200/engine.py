@@ -114,6 +114,15 @@ class Engine:
         of the ids (legacy HF configs with ``eos_token_id == 2``, OpenAI clip).  See ``plip_set_text_pooling``."""
         check(self._L.plip_set_text_pooling(self._h, int(bool(no_eos_argmax))), "plip_set_text_pooling")
 
+    def set_last_layer_pruning(self, on: bool) -> None:
+        """Embedding calls run the last encoder layer's out_proj / LayerNorm 2 / MLP on the pooled rows only (CLS, first
+        eos) — same embeddings, less work; hidden-state requests are never pruned.  See ``plip_set_last_layer_pruning``."""
+        check(self._L.plip_set_last_layer_pruning(self._h, int(bool(on))), "plip_set_last_layer_pruning")
+
+    @property
+    def last_layer_pruning(self) -> bool:
+        return bool(self._L.plip_last_layer_pruning(self._h))
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._L.plip_destroy(self._h)

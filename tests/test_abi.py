@@ -28,7 +28,7 @@ def test_header_symbols_all_exported_and_bound():
 
 def test_abi_version_and_layout_queries():
     L = _lib.lib()
-    assert L.plip_abi_version() == 4
+    assert L.plip_abi_version() == 5
     n = L.plip_weights_num_tensors()
     assert n == 5 + 12 * 10 + 3 + 2 + 12 * 10 + 3
     prev_end = 0

@@ -179,6 +179,45 @@ def test_small_batch_graph_replay_is_bit_identical(engine, state_dict):
     assert (1 - O.cosine(engine.encode_images(px[:3]).cpu(), e1[:3].cpu())).max().item() < 1e-6   # another n / graph
 
 
+def test_last_layer_pruning_gives_the_same_embeddings(engine, state_dict):
+    """plip_set_last_layer_pruning: the last layer's out_proj / LN2 / MLP on the pooled rows only.  Per-row arithmetic is
+    unchanged (only the grouping of the LayerNorm-statistics partials can differ with the tile shape), so the
+    embeddings must agree with the full run to fp32 rounding — eager (n > 128, several micro-batches), graph replay
+    (n <= 128), ragged eos positions, masks, short sequences, no-eos rows — and hidden states must not change."""
+    px = synth.pixel_values(8, seed=61).cuda()
+    pxl = synth.pixel_values(150, seed=62).cuda()
+    ids, mask = synth.token_ids(8, seed=63, min_len=4)
+    idl, maskl = synth.token_ids(150, seed=64, min_len=3)
+    mask2 = maskl.clone(); mask2[:, 1:3] = 0
+    noeos = ids.clone(); noeos[noeos == 49407] = 17; noeos[:, 0] = 1234
+    short = ids[:, :24].clone(); short[:, 23] = 49407
+    assert not engine.last_layer_pruning
+    def run():
+        return [engine.encode_images(px).clone(), engine.encode_images(px).clone(), engine.encode_images(pxl).clone(),
+                engine.encode_images(pxl, normalize=True).clone(),
+                engine.encode_text(ids.cuda(), mask.cuda()).clone(), engine.encode_text(ids.cuda(), mask.cuda()).clone(),
+                engine.encode_text(idl.cuda(), mask2.cuda()).clone(), engine.encode_text(idl.cuda()).clone(),
+                engine.encode_text(noeos.cuda()).clone(), engine.encode_text(short.cuda()).clone(),
+                engine.encode_text(idl.cuda(), maskl.cuda(), prefix_len=int(maskl.sum(1).max())).clone(),
+                engine.encode_text_host(idl, maskl).clone(), engine.encode_images_host(pxl.cpu()).clone()]
+    full = run()
+    hv = engine.hidden_states("vision", px, 12).clone()
+    engine.set_last_layer_pruning(True)
+    try:
+        assert engine.last_layer_pruning
+        pruned = run()
+        assert torch.equal(engine.hidden_states("vision", px, 12), hv)
+    finally:
+        engine.set_last_layer_pruning(False)
+    for i, (a, b) in enumerate(zip(full, pruned)):
+        assert a.shape == b.shape
+        rel = ((a - b).abs().max() / a.abs().max()).item()
+        assert rel < 2e-5, (i, rel)
+    assert (1 - O.cosine(pruned[2].cpu(), O.get_image_features(state_dict, pxl.cpu()))).max().item() < COS_TOL
+    assert (1 - O.cosine(pruned[6].cpu(), O.get_text_features(state_dict, idl, mask2))).max().item() < COS_TOL
+    assert torch.equal(run()[0], full[0])                       # switched off again: the unpruned graph is replayed
+
+
 def test_forward_on_host_inputs_equals_device_inputs(state_dict):
     """`model(**inputs)` with HOST tensors (the e2e path of bench.py): pixels are uploaded micro-batch by micro-batch on
     the engine's copy stream while the text tower / the previous micro-batch computes — same logits, bit for bit."""
