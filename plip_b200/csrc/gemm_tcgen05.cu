@@ -163,11 +163,14 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, f
 }
 
 // One accumulator tile (this warp's 32 rows x BN columns) -> global memory.
-template <int BN, int EPI, bool F16>
-__device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMap* tmC, uint32_t tmem_row_base,
+// `release_bar`: the accumulator's "empty" barrier (cluster address of the pair leader's for CG == 2).  The 16-bit-output
+// path arrives on it itself, as soon as its last TMEM load has landed (before the remaining math and stores), and
+// returns true; the other paths return false and the caller releases the accumulator after the call.
+template <int CG, int BN, int EPI, bool F16>
+__device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMap* tmC, uint32_t tmem_row_base,
                                               uint32_t stage_smem,
                                               uint32_t bias_smem, uint32_t rpf_smem, int row_base, int col_base, int n_blk,
-                                              int half, int lane, float ln_mean, float ln_rstd) {
+                                              int half, int lane, float ln_mean, float ln_rstd, uint32_t release_bar) {
   constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   constexpr bool GELU = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD);
@@ -184,7 +187,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
       for (int i = 0; i < 32; ++i) acc ^= v[i];
     }
     if (acc == 0x12345678u && p.M < 0) reinterpret_cast<uint32_t*>(p.out)[0] = acc;  // keep the loads alive
-    return;
+    return false;
   }
   const uint32_t my_row = stage_smem + lane * 128;
   const int sw = lane & 7;
@@ -192,6 +195,105 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
   const int rb_chunk = lane & 7;  // read-back: 16-byte chunk of the row
 
   if constexpr (OUT_BF16) {
+#ifndef PLIP_EPI_R2_ORDER
+    // Software pipeline over 32-column pieces (r2 probe, profiles/r2_notes.md §9: the epilogue, not the MMAs, paced the
+    // short-K GEMMs — all eight warps loaded, then all computed, then all stored, so TMEM-read bandwidth (64 B/clk),
+    // MUFU / FMA issue and the store wait never overlapped).  A warp always has the NEXT piece's tcgen05.ld in flight
+    // while it runs the math of the current one; the accumulator is handed back to the MMA warp as soon as the last
+    // piece has landed in registers, i.e. before that piece's math and the last store.
+    constexpr int kMaxBlk = (BN / 64 + 1) / 2;            // 64-column blocks a warp may own (half, half + 2, ...)
+    const int nblk = (BN / 64 - half + 1) / 2;
+    uint32_t va[32], vb[32];
+    tmem_ld32(tmem_row_base + half * 64, va);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < kMaxBlk; ++j) {
+      if (j >= nblk) break;
+      const int blk = half + 2 * j;
+      const bool more = j + 1 < nblk;
+      uint32_t pk[32];
+      float dbg_acc = 0.f;
+      tmem_ld32(tmem_row_base + blk * 64 + 32, vb);       // in flight during the first half's math
+      {
+        float2 f[16];
+        acc_math32<HAS_BIAS, LN_FOLD, BN>(va, bias_smem + (j * 64) * 4, mean, rstd, f);
+        if (p.dbg >= 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dbg_acc += f[i].x + f[i].y;
+        } else {
+          if constexpr (GELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = quick_gelu2(f[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_op2<F16>(f[i].x, f[i].y);
+        }
+      }
+      tmem_ld_wait();
+      if (more) {
+        tmem_ld32(tmem_row_base + (blk + 2) * 64, va);    // next block's first half: in flight during this math + store
+      } else {
+        // every accumulator column this warp owns is in registers: release the TMEM buffer now
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) mbar_arrive(release_bar);
+          else mbar_arrive_cluster(release_bar);
+        }
+      }
+      {
+        float2 f[16];
+        acc_math32<HAS_BIAS, LN_FOLD, BN>(vb, bias_smem + (j * 64 + 32) * 4, mean, rstd, f);
+        if (p.dbg >= 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dbg_acc += f[i].x + f[i].y;
+        } else {
+          if constexpr (GELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = quick_gelu2(f[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[16 + i] = pack_op2<F16>(f[i].x, f[i].y);
+        }
+      }
+      if (p.dbg >= 2) {
+        if (dbg_acc == 1.2345e30f) reinterpret_cast<float*>(p.out)[0] = dbg_acc;
+      } else {
+        if (p.tma_store) {  // the previous bulk store must have finished reading this staging block
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int chunk = 0; chunk < 8; ++chunk)
+          st_shared_v4(my_row + ((chunk ^ sw) << 4), pk[4 * chunk + 0], pk[4 * chunk + 1], pk[4 * chunk + 2], pk[4 * chunk + 3]);
+        if (p.tma_store) {
+          // the staging block is laid out exactly as a SWIZZLE_128B [32 rows x 64 bf16] TMA box
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && p.dbg != 1) {
+            tma_store_2d(tmC, stage_smem, col_base + blk * 64, row_base);
+            tma_store_commit();
+          }
+        } else {
+          __syncwarp();
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rb_row;
+            const uint4 v = ld_shared_v4(stage_smem + r * 128 + ((rb_chunk ^ (r & 7)) << 4));
+            const int grow = row_base + r;
+            if (grow < p.M && p.dbg != 1)
+              *reinterpret_cast<uint4*>(out + static_cast<size_t>(grow) * p.ldo + col_base + blk * 64 + rb_chunk * 8) = v;
+          }
+          __syncwarp();
+        }
+      }
+      if (more) tmem_ld_wait();
+    }
+    // (no wait for the last bulk store here: the next tile's first block waits before it touches the staging block,
+    //  and the kernel ends with tma_store_wait_all)
+    return true;
+#else   // A/B build switch: the epilogue order of the first half of round 2 (load both halves, compute, store, per block)
 #pragma unroll 1
     for (int blk = half; blk < BN / 64; blk += 2) {
       // 64 columns -> 128 B of bf16 per row.  The math runs BEFORE the wait for the previous bulk store of this
@@ -261,6 +363,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
     }
     if (p.tma_store && lane == 0) tma_store_wait_read();  // staging is reused by the next tile right away
     __syncwarp();
+    return false;
+#endif
   } else {
     // per-row (sum, sum of squares) of the updated residual rows this lane writes (rows i*4 + rb_row)
     float st1[8], st2[8];
@@ -368,6 +472,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, const CUtensorMa
       }
     }
   }
+  return false;
 }
 
 // QUAD (experimental, PLIP_GEMM_QUAD=1): a cluster of TWO CTA pairs works on neighbouring M blocks of the same N block
@@ -578,14 +683,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      epilogue_tile<BN, EPI, F16>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + warp * C::VEC_BYTES,
-                                  rpf_base + warp * 8192u, row_base,
-                             n_blk * BN, n_blk, half, lane, ln_mean, ln_rstd);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 1) mbar_arrive(tempty_bar(a));
-        else mbar_arrive_cluster(mapa_shared(tempty_bar(a), lead_rank));
+      uint32_t release_bar = tempty_bar(a);
+      if constexpr (CG == 2) release_bar = mapa_shared(release_bar, lead_rank);
+      const bool released =
+          epilogue_tile<CG, BN, EPI, F16>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + warp * C::VEC_BYTES,
+                                          rpf_base + warp * 8192u, row_base, n_blk * BN, n_blk, half, lane, ln_mean, ln_rstd,
+                                          release_bar);
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) mbar_arrive(release_bar);
+          else mbar_arrive_cluster(release_bar);
+        }
       }
       a ^= 1;
       if (a == 0) aph ^= 1u;
