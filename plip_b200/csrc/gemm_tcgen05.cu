@@ -72,6 +72,7 @@ struct Cfg {
 struct GemmDev {
   int M, N, K;
   int tma_store;  // bf16 epilogues: write the staged blocks with TMA bulk stores instead of read-back + STG
+  int f32_serial;  // A/B switch (PLIP_GEMM_F32_SERIAL=1): fp32-output epilogues load each block from TMEM right before its math
   int dbg;  // diagnostic (PLIP_GEMM_DBG): 1 = no global stores, 2 = no staging and no stores, 3 = no math either
   const float* bias;
   const float* rowscale;
@@ -379,6 +380,16 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
     constexpr bool RPF = (EPI == EPI_BIAS_RESID_F32) && (BN < 256);  // == Cfg::RPF
 #endif
     int jblk = 0;
+#ifndef PLIP_EPI_R2_ORDER
+    // same software pipeline as the 16-bit path: the next block's accumulator columns are on their way from TMEM while
+    // this block is staged, read back and stored; the accumulator is released once the last block is in registers
+    uint32_t vacc[32];
+    const bool pipe = p.f32_serial == 0;
+    if (pipe) {
+      tmem_ld32(tmem_row_base + half * 32, vacc);
+      tmem_ld_wait();
+    }
+#endif
 #pragma unroll 1
     for (int blk = half; blk < BN / 32; blk += 2, ++jblk) {
       // 32 columns -> 128 B of fp32 per row
@@ -404,7 +415,25 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
       }
       {
         float2 f[16];
+#ifndef PLIP_EPI_R2_ORDER
+        if (!pipe) {
+          tmem_ld32(tmem_row_base + blk * 32, vacc);
+          tmem_ld_wait();
+        }
+        acc_math32<HAS_BIAS, false, BN>(vacc, bias_smem + (blk >> 1) * 32 * 4, 0.f, 1.f, f);
+        if (has_next) {
+          if (pipe) tmem_ld32(tmem_row_base + (blk + 2) * 32, vacc);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 1) mbar_arrive(release_bar);
+            else mbar_arrive_cluster(release_bar);
+          }
+        }
+#else
         load_acc32<HAS_BIAS, false, BN>(tmem_row_base + blk * 32, bias_smem + (blk >> 1) * 32 * 4, 0.f, 1.f, f);
+#endif
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           st_shared_v4(my_row + ((c ^ sw) << 4), __float_as_uint(f[2 * c + 0].x), __float_as_uint(f[2 * c + 0].y),
@@ -453,6 +482,9 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
           }
         }
       }
+#ifndef PLIP_EPI_R2_ORDER
+      if (has_next && pipe) tmem_ld_wait();
+#endif
       __syncwarp();
     }
     if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -472,7 +504,11 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
       }
     }
   }
+#ifndef PLIP_EPI_R2_ORDER
+  return true;
+#else
   return false;
+#endif
 }
 
 // QUAD (experimental, PLIP_GEMM_QUAD=1): a cluster of TWO CTA pairs works on neighbouring M blocks of the same N block
@@ -771,6 +807,8 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   p.M = g.M; p.N = g.N; p.K = g.K;
   static const int env_dbg = env_int("PLIP_GEMM_DBG", 0);
   p.dbg = env_dbg;
+  static const int env_f32_serial = env_int("PLIP_GEMM_F32_SERIAL", 0);
+  p.f32_serial = env_f32_serial;
   p.tma_store = tma_store ? 1 : 0;
   p.bias = g.bias; p.rowscale = g.rowscale; p.out = g.out; p.ldo = g.ldo; p.pos = g.pos;
   p.colsum = g.colsum; p.stats_in = g.stats_in; p.n_partials = g.n_partials;
