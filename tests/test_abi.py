@@ -29,6 +29,9 @@ def test_header_symbols_all_exported_and_bound():
 def test_abi_version_and_layout_queries():
     L = _lib.lib()
     assert L.plip_abi_version() == 5
+    hdr = open(os.path.join(ROOT, "include", "plip_b200.h")).read()
+    assert int(re.search(r"#define\s+PLIP_B200_ABI_VERSION\s+(\d+)", hdr).group(1)) == 5
+
     n = L.plip_weights_num_tensors()
     assert n == 5 + 12 * 10 + 3 + 2 + 12 * 10 + 3
     prev_end = 0
@@ -109,3 +112,12 @@ def test_argument_validation_needs_no_gpu():
         assert msg in _lib.last_error(), _lib.last_error()
     assert L.plip_resize_crop_u8(addr + 1, 256, C.byref(_lib.ResizeDesc(0, 5, 5, 224, 224, 0, 0)), 1, addr, None) != 0
     assert "aligned" in _lib.last_error()
+
+
+def test_graft_entry_build_check_follows_the_header():
+    """__graft_entry__.build() compares the library's ABI version with the header's (a hard-coded number there broke
+    the driver's build check when the ABI moved to 5)."""
+    import inspect
+    import __graft_entry__ as g
+    src = inspect.getsource(g.build)
+    assert "PLIP_B200_ABI_VERSION" in src and "== 4" not in src and "== 5" not in src
