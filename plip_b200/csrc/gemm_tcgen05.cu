@@ -154,14 +154,6 @@ __device__ __forceinline__ void acc_math32(const uint32_t (&v)[32], uint32_t bia
     }
   }
 }
-template <bool HAS_BIAS, bool LN_FOLD, int BN>
-__device__ __forceinline__ void load_acc32(uint32_t taddr, uint32_t bias_smem, float nrm, float rstd,
-                                           float2 (&f)[16]) {
-  uint32_t v[32];
-  tmem_ld32(taddr, v);
-  tmem_ld_wait();
-  acc_math32<HAS_BIAS, LN_FOLD, BN>(v, bias_smem, nrm, rstd, f);
-}
 
 // One accumulator tile (this warp's 32 rows x BN columns) -> global memory.
 // `release_bar`: the accumulator's "empty" barrier (cluster address of the pair leader's for CG == 2).  The 16-bit-output
@@ -196,7 +188,6 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
   const int rb_chunk = lane & 7;  // read-back: 16-byte chunk of the row
 
   if constexpr (OUT_BF16) {
-#ifndef PLIP_EPI_R2_ORDER
     // Software pipeline over 32-column pieces (r2 probe, profiles/r2_notes.md §9: the epilogue, not the MMAs, paced the
     // short-K GEMMs — all eight warps loaded, then all computed, then all stored, so TMEM-read bandwidth (64 B/clk),
     // MUFU / FMA issue and the store wait never overlapped).  A warp always has the NEXT piece's tcgen05.ld in flight
@@ -294,78 +285,6 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
     // (no wait for the last bulk store here: the next tile's first block waits before it touches the staging block,
     //  and the kernel ends with tma_store_wait_all)
     return true;
-#else   // A/B build switch: the epilogue order of the first half of round 2 (load both halves, compute, store, per block)
-#pragma unroll 1
-    for (int blk = half; blk < BN / 64; blk += 2) {
-      // 64 columns -> 128 B of bf16 per row.  The math runs BEFORE the wait for the previous bulk store of this
-      // warp's staging block, so the store's smem read (and the TMEM load) overlap instead of serialising.
-      uint32_t pk[32];
-      {
-        // both 32-column halves of the block are loaded from TMEM before the single wait, and their math is
-        // independent: two TMEM latencies and two dependency chains overlap instead of running back to back
-        uint32_t v0[32], v1[32];
-        tmem_ld32(tmem_row_base + blk * 64, v0);
-#ifdef PLIP_EPI_SERIAL_LD   // A/B build switch (tools/r2_call10.sh): the round-1 order, one wait per half
-        tmem_ld_wait();
-#endif
-        tmem_ld32(tmem_row_base + blk * 64 + 32, v1);
-        tmem_ld_wait();
-        float2 f0[16], f1[16];
-        acc_math32<HAS_BIAS, LN_FOLD, BN>(v0, bias_smem + ((blk >> 1) * 64) * 4, mean, rstd, f0);
-        acc_math32<HAS_BIAS, LN_FOLD, BN>(v1, bias_smem + ((blk >> 1) * 64 + 32) * 4, mean, rstd, f1);
-        if (p.dbg >= 2) {
-          float a = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) a += (f0[i].x + f0[i].y) + (f1[i].x + f1[i].y);
-          if (a == 1.2345e30f) reinterpret_cast<float*>(p.out)[0] = a;
-          continue;
-        }
-        if constexpr (GELU) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            f0[i] = quick_gelu2(f0[i]);
-            f1[i] = quick_gelu2(f1[i]);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          pk[i] = pack_op2<F16>(f0[i].x, f0[i].y);
-          pk[16 + i] = pack_op2<F16>(f1[i].x, f1[i].y);
-        }
-      }
-      if (p.tma_store) {  // the previous bulk store must have finished reading this staging block
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-      }
-#pragma unroll
-      for (int chunk = 0; chunk < 8; ++chunk)
-        st_shared_v4(my_row + ((chunk ^ sw) << 4), pk[4 * chunk + 0], pk[4 * chunk + 1], pk[4 * chunk + 2], pk[4 * chunk + 3]);
-      if (p.tma_store) {
-        // the staging block is laid out exactly as a SWIZZLE_128B [32 rows x 64 bf16] TMA box
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && p.dbg != 1) {
-          tma_store_2d(tmC, stage_smem, col_base + blk * 64, row_base);
-          tma_store_commit();
-        }
-        continue;
-      }
-      __syncwarp();
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + rb_row;
-        const uint4 v = ld_shared_v4(stage_smem + r * 128 + ((rb_chunk ^ (r & 7)) << 4));
-        const int grow = row_base + r;
-        if (grow < p.M && p.dbg != 1)
-          *reinterpret_cast<uint4*>(out + static_cast<size_t>(grow) * p.ldo + col_base + blk * 64 + rb_chunk * 8) = v;
-      }
-      __syncwarp();
-    }
-    if (p.tma_store && lane == 0) tma_store_wait_read();  // staging is reused by the next tile right away
-    __syncwarp();
-    return false;
-#endif
   } else {
     // per-row (sum, sum of squares) of the updated residual rows this lane writes (rows i*4 + rb_row)
     float st1[8], st2[8];
@@ -380,7 +299,6 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
     constexpr bool RPF = (EPI == EPI_BIAS_RESID_F32) && (BN < 256);  // == Cfg::RPF
 #endif
     int jblk = 0;
-#ifndef PLIP_EPI_R2_ORDER
     // same software pipeline as the 16-bit path: the next block's accumulator columns are on their way from TMEM while
     // this block is staged, read back and stored; the accumulator is released once the last block is in registers
     uint32_t vacc[32];
@@ -389,7 +307,6 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
       tmem_ld32(tmem_row_base + half * 32, vacc);
       tmem_ld_wait();
     }
-#endif
 #pragma unroll 1
     for (int blk = half; blk < BN / 32; blk += 2, ++jblk) {
       // 32 columns -> 128 B of fp32 per row
@@ -415,7 +332,6 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
       }
       {
         float2 f[16];
-#ifndef PLIP_EPI_R2_ORDER
         if (!pipe) {
           tmem_ld32(tmem_row_base + blk * 32, vacc);
           tmem_ld_wait();
@@ -431,9 +347,6 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
             else mbar_arrive_cluster(release_bar);
           }
         }
-#else
-        load_acc32<HAS_BIAS, false, BN>(tmem_row_base + blk * 32, bias_smem + (blk >> 1) * 32 * 4, 0.f, 1.f, f);
-#endif
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           st_shared_v4(my_row + ((c ^ sw) << 4), __float_as_uint(f[2 * c + 0].x), __float_as_uint(f[2 * c + 0].y),
@@ -482,9 +395,7 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
           }
         }
       }
-#ifndef PLIP_EPI_R2_ORDER
       if (has_next && pipe) tmem_ld_wait();
-#endif
       __syncwarp();
     }
     if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -504,11 +415,7 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
       }
     }
   }
-#ifndef PLIP_EPI_R2_ORDER
   return true;
-#else
-  return false;
-#endif
 }
 
 // QUAD (experimental, PLIP_GEMM_QUAD=1): a cluster of TWO CTA pairs works on neighbouring M blocks of the same N block
