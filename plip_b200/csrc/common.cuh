@@ -74,9 +74,6 @@ inline bool first_use_on_device(unsigned long long& mask) {
 // Encode a 2-D bf16 row-major tensor map with 128-byte swizzle.
 // dims: inner (contiguous) extent `cols`, outer extent `rows`, row stride in bytes.
 // box: box_cols (must be 64 bf16 == 128 B for SWIZZLE_128B) x box_rows (<=256).
-// bf16 NCHW pixels [n, 3, 224, 224] seen as patches: dims (kx 32, ky 32, px 7, u = py + 7 c + 21 b), box [32, 2, 7, 1]
-// = the [7 patch rows x 64 k] piece of the im2col matrix for one (image, patch row, channel, ky pair), SWIZZLE_128B.
-int make_tmap_patch_bf16(CUtensorMap* out, const void* pixels, uint64_t n_images);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);
 
@@ -234,16 +231,6 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtenso
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0),
       "r"(c1)
-      : "memory");
-}
-
-// 4-D box load for a CTA pair (the im2col-free patch-embedding A operand, gemm_tcgen05.cu).
-__device__ __forceinline__ void tma_load_4d_cg2(uint32_t smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr,
-                                                int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 

@@ -383,18 +383,13 @@ int vision_trunk(plip_engine* e, const void* pixels, int fmt, int64_t mb, int nu
                  bool prune = false) {
   e->prof_tower = 0;
   const double dmb = (double)mb;
-  // PLIP_PATCH_DIRECT=1 (opt-in): bf16 NCHW pixels feed the patch GEMM straight through a 4-D tensor map
-  // (gemm_tcgen05.cu, "direct patch embedding") — no im2col matrix.  Other pixel formats need the conversion pass.
-  static const int env_direct = [] { const char* v = getenv("PLIP_PATCH_DIRECT"); return v ? atoi(v) : 0; }();
-  const bool direct = env_direct != 0 && fmt == PLIP_PIX_BF16_NCHW && !e->f16;
-  if (!direct) {
+  {
     ProfScope ps(e, st, PK_IM2COL, 0, dmb * (double)pixel_bytes(fmt) + dmb * kPatches * kPatchK * 2);
     if (int rc = launch_im2col(pixels, fmt, mb, e->H, e->f16, st)) return rc;
   }
   GemmArgs g;
   g.f16 = e->f16;
   g.A = e->H; g.lda = kPatchK; g.W = e->v_patch_w; g.ldw = kPatchK;
-  if (direct) { g.patch_pixels = pixels; g.patch_images = (int)mb; }
   g.M = (int)(mb * kPatches); g.N = kVisDim; g.K = kPatchK;
   g.out = e->X; g.ldo = kVisDim; g.pos = e->v_pos; g.epi = EPI_PATCH_F32;
   {

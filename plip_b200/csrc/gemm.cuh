@@ -37,8 +37,6 @@ struct GemmArgs {
   void* out = nullptr;               // bf16 or fp32 depending on epilogue; row stride ldo elements
   int ldo = 0;
   const float* pos = nullptr;        // EPI_PATCH_F32: vision position embedding [50, N]
-  const void* patch_pixels = nullptr;  // EPI_PATCH_F32 (optional): bf16 NCHW pixels [patch_images,3,224,224] — the A operand
-  int patch_images = 0;                //   is then read straight from the images (no im2col matrix; A / lda are ignored)
   const float* colsum = nullptr;     // EPI_LN_*: [N] row sums of the folded bf16 weight
   const float2* stats_in = nullptr;  // EPI_LN_*: [M, kStatSlots] partial (sum, sumsq) of the fp32 rows behind A
   int n_partials = 0;                // EPI_LN_*: valid slots in stats_in

@@ -84,7 +84,6 @@ struct GemmDev {
   int n_partials;
   __nv_bfloat16* xb_out;
   float2* stats_out;
-  int patch_direct;  // EPI_PATCH_F32: tmA is the 4-D patch view of the pixels; a CTA owns 18 patch-row groups = 126 rows
 };
 
 // ---- epilogue ---------------------------------------------------------------------------------
@@ -164,8 +163,7 @@ template <int CG, int BN, int EPI, bool F16>
 __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMap* tmC, uint32_t tmem_row_base,
                                               uint32_t stage_smem,
                                               uint32_t bias_smem, uint32_t rpf_smem, int row_base, int col_base, int n_blk,
-                                              int half, int lane, float ln_mean, float ln_rstd, uint32_t release_bar,
-                                              int row_limit = 32) {
+                                              int half, int lane, float ln_mean, float ln_rstd, uint32_t release_bar) {
   constexpr bool LN_FOLD = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   constexpr bool GELU = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_GELU_BF16);
   constexpr bool HAS_BIAS = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || LN_FOLD);
@@ -364,9 +362,7 @@ __device__ __forceinline__ bool epilogue_tile(const GemmDev& p, const CUtensorMa
         float4 v = ld_shared_f4(stage_smem + r * 128 + ((rb_chunk ^ (r & 7)) << 4));
         const int grow = row_base + r;
         if constexpr (RPF) xr[i] = ld_shared_f4(rpf_cur + r * 128 + rb_chunk * 16);  // this lane's own copies
-        bool live = grow < p.M;
-        if constexpr (EPI == EPI_PATCH_F32) live = live && r < row_limit;   // direct patch tiles own 126 of their 128 rows
-        if (live) {
+        if (grow < p.M) {
           if constexpr (EPI == EPI_BIAS_RESID_F32) {
             const float2 y01 = __fadd2_rn(make_float2(xr[i].x, xr[i].y), make_float2(v.x, v.y));
             const float2 y23 = __fadd2_rn(make_float2(xr[i].z, xr[i].w), make_float2(v.z, v.w));
@@ -481,14 +477,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base =
       *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_raw_u32));
 
-  // Direct patch embedding (EPI_PATCH_F32 on a CTA pair, p.patch_direct): the A operand is read from the images through a
-  // 4-D tensor map.  7 patches of one patch row form a [7 x 64] box per k-block, so a CTA owns 18 such groups = 126
-  // rows of its 128-row UMMA operand (rows 126, 127 are never written nor stored) and a pair tile covers 252 rows.
-  constexpr bool kPatchCapable = (EPI == EPI_PATCH_F32) && (CG == 2) && !QUAD;
-  const bool patch_direct = kPatchCapable && p.patch_direct != 0;
-  constexpr int kPatchGroups = 18, kPatchRows = kPatchGroups * 7;
   const int num_n_blk = p.N / BN;
-  const int num_m_blk = patch_direct ? (p.M + kPatchRows * CG - 1) / (kPatchRows * CG) : (p.M + BM * CG - 1) / (BM * CG);
+  const int num_m_blk = (p.M + BM * CG - 1) / (BM * CG);
   // QUAD: a work item is a pair of neighbouring M blocks x one N block; an odd M-block count leaves the second pair of the
   // last item with rows past M only (zero-filled loads, nothing stored)
   const int num_tiles = (QUAD ? (num_m_blk + 1) / 2 : num_m_blk) * num_n_blk;
@@ -497,38 +487,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int tile_step = gridDim.x / CL;
   auto m_block_of = [&](int t) { const int mb = t / num_n_blk; return QUAD ? 2 * mb + (int)pair : mb; };
 
-  if (warp == kWarpTma && patch_direct) {
-    // ===================== TMA producer, direct patch embedding =====================
-    // k-block kb = (channel c = kb / 16, ky pair kb % 16); group g = (image b, patch row py); box coordinate
-    // (kx 0, ky 2 (kb % 16), px 0, u = py + 7 c + 21 b) lands as rows 7 j .. 7 j + 6 of the K-major SWIZZLE_128B tile
-    // (the swizzle is a function of the shared-memory address, so 128-byte-aligned pieces compose the same tile a
-    // single [128 x 64] box would).  Lanes 0..17 issue one box each; groups past the last image are zero-filled.
-    if constexpr (kPatchCapable) {
-      int s = 0;
-      uint32_t ph = 0;
-      constexpr uint32_t kABytes = kPatchGroups * 7 * 128;
-      for (int t = tile0; t < num_tiles; t += tile_step) {
-        const int m_blk = m_block_of(t), n_blk = t % num_n_blk;
-        const int g = (m_blk * CG + (int)cta_rank) * kPatchGroups + lane;
-        const int gb = g / 7, gpy = g - gb * 7;
-        const int n0 = n_blk * BN + cta_rank * C::LOAD_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (lane == 0) mbar_wait(empty_bar(s), ph ^ 1u);
-          __syncwarp();
-          const uint32_t sa = smem_base + s * C::STAGE;
-          const uint32_t lfull = mapa_shared(full_bar(s), lead_rank);
-          if (lane == 0) {
-            if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * (kABytes + C::B_STAGE));
-            else mbar_arrive_cluster(lfull);
-            tma_load_2d_cg2(sa + A_STAGE, &tmB, lfull, kb * BK, n0);
-          }
-          if (lane < kPatchGroups)
-            tma_load_4d_cg2(sa + lane * (7 * 128), &tmA, lfull, 0, 2 * (kb & 15), 0, gpy + 7 * (kb >> 4) + 21 * gb);
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == kWarpTma) {
+  if (warp == kWarpTma) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;
@@ -623,8 +582,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         __syncwarp();
       }
-      const int row_base = patch_direct ? (m_blk * CG + (int)cta_rank) * kPatchRows + q * 32
-                                        : m_blk * BM * CG + cta_rank * BM + q * 32;
+      const int row_base = m_blk * BM * CG + cta_rank * BM + q * 32;
       if constexpr (C::RPF)  // first residual block of the tile -> prefetch buffer 0, while the MMAs of the tile run
         rpf_issue(reinterpret_cast<const float*>(p.out), p.ldo, p.M, rpf_base + warp * 8192u, row_base, n_blk * BN + half * 32, lane);
       if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -673,7 +631,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool released =
           epilogue_tile<CG, BN, EPI, F16>(p, &tmC, trow, epi_base + warp * kEpiStageBytes, bias_base + warp * C::VEC_BYTES,
                                           rpf_base + warp * 8192u, row_base, n_blk * BN, n_blk, half, lane, ln_mean, ln_rstd,
-                                          release_bar, (patch_direct ? kPatchRows : BM) - q * 32);
+                                          release_bar);
       if (!released) {
         tc_fence_before();
         __syncwarp();
@@ -742,10 +700,7 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
               C::STAGES, C::SMEM_BYTES, max_groups);
   }
   CUtensorMap tmA, tmB;
-  const bool patch_direct = (EPI == EPI_PATCH_F32) && CG == 2 && !QUAD && g.patch_pixels != nullptr;
-  if (patch_direct) {
-    if (int rc = make_tmap_patch_bf16(&tmA, g.patch_pixels, (uint64_t)g.patch_images)) return rc;
-  } else if (int rc = make_tmap_bf16_2d(&tmA, g.A, g.M, g.K, (uint64_t)g.lda * 2, BM, BK)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tmA, g.A, g.M, g.K, (uint64_t)g.lda * 2, BM, BK)) return rc;
   if (int rc = make_tmap_bf16_2d(&tmB, g.W, g.N, g.K, (uint64_t)g.ldw * 2, C::LOAD_N, BK)) return rc;
   constexpr bool kOutBf16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_BF16 ||
                              EPI == EPI_LN_BIAS_GELU_BF16);
@@ -761,7 +716,6 @@ int launch_inst(const GemmArgs& g, cudaStream_t stream) {
   p.dbg = env_dbg;
   static const int env_f32_serial = env_int("PLIP_GEMM_F32_SERIAL", 0);
   p.f32_serial = env_f32_serial;
-  p.patch_direct = patch_direct ? 1 : 0;
   p.tma_store = tma_store ? 1 : 0;
   p.bias = g.bias; p.rowscale = g.rowscale; p.out = g.out; p.ldo = g.ldo; p.pos = g.pos;
   p.colsum = g.colsum; p.stats_in = g.stats_in; p.n_partials = g.n_partials;
@@ -831,10 +785,6 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
                  "launch_gemm: xb/stats outputs belong to the residual epilogue");
   static const int env_cg = env_int("PLIP_GEMM_CG", 0);
   static const int env_bn = env_int("PLIP_GEMM_BN", 0);
-  if (g.patch_pixels)
-    PLIP_REQUIRE(g.epi == EPI_PATCH_F32 && !g.f16 && !g.force_cg && !env_cg && g.K == kPatchK &&
-                 g.M == g.patch_images * kPatches && (reinterpret_cast<uintptr_t>(g.patch_pixels) & 15) == 0,
-                 "launch_gemm: the direct patch operand needs the bf16 patch-embedding GEMM on CTA pairs (M = 49 images, K = 3072)");
   int cg = g.force_cg ? g.force_cg : (env_cg ? env_cg : 2);
   int bn = g.force_bn ? g.force_bn : (env_bn ? env_bn : 256);
   // Memory-bound residual GEMM with a short K (out_proj): 192-wide tiles quantise better on 74 CTA

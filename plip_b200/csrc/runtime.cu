@@ -90,38 +90,6 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
-int make_tmap_patch_bf16(CUtensorMap* out, const void* pixels, uint64_t n_images) {
-  const TmapKey key{reinterpret_cast<uint64_t>(pixels), n_images, 0xFFFFFFFFull /* marks the patch view */, 0, 0};
-  {
-    std::lock_guard<std::mutex> lk(g_tmap_mu);
-    auto it = g_tmap_cache.find(key);
-    if (it != g_tmap_cache.end()) {
-      *out = it->second;
-      return 0;
-    }
-  }
-  EncodeTiledFn enc = resolve_encode();
-  if (!enc) return -1;
-  // element offset of pixel (b, c, 32 py + ky, 32 px + kx) = kx + 224 ky + 32 px + 7168 (py + 7 c + 21 b):
-  // 7 patch rows are exactly one channel plane (7 * 32 * 224 = 224 * 224), so (py, c, b) fold into ONE dimension
-  cuuint64_t gdim[4] = {32, 32, 7, 21 * n_images};
-  cuuint64_t gstr[3] = {224 * 2, 32 * 2, 7168 * 2};
-  cuuint32_t box[4] = {32, 2, 7, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(pixels), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled (patch view) failed (%d): pixels=%p images=%llu", (int)r, pixels,
-                   (unsigned long long)n_images);
-    return -1;
-  }
-  std::lock_guard<std::mutex> lk(g_tmap_mu);
-  if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();
-  g_tmap_cache.emplace(key, *out);
-  return 0;
-}
-
 static int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                                uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn enc = resolve_encode();

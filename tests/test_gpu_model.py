@@ -218,40 +218,6 @@ def test_last_layer_pruning_gives_the_same_embeddings(engine, state_dict):
     assert torch.equal(run()[0], full[0])                       # switched off again: the unpruned graph is replayed
 
 
-def test_direct_patch_embedding_is_bit_identical(engine, tmp_path):
-    """PLIP_PATCH_DIRECT=1 (opt-in): bf16 NCHW pixels feed the patch-embedding GEMM through a 4-D tensor map instead of
-    the im2col matrix.  Same operand values, same accumulation order per output row -> the embeddings layer (hidden
-    state 0) and the image embeddings must equal the default path bit for bit: partial tiles (5 images), several
-    micro-batches (150 images at max_micro_batch 64) and the graph replay."""
-    import os
-    import subprocess
-    import sys
-    px5 = synth.pixel_values(5, seed=71).to(torch.bfloat16)
-    px150 = synth.pixel_values(150, seed=72).to(torch.bfloat16)
-    ref = {"h0": engine.hidden_states("vision", px5.cuda(), 0).cpu(), "e5": engine.encode_images(px5.cuda()).cpu(),
-           "e5b": engine.encode_images(px5.cuda()).cpu(), "e150": engine.encode_images(px150.cuda()).cpu()}
-    script = tmp_path / "direct.py"
-    script.write_text(
-        "import sys, torch\n"
-        "sys.path.insert(0, %r)\n"
-        "from oracle import synth\n"
-        "from plip_b200 import synthetic\n"
-        "from plip_b200.engine import Engine\n"
-        "eng = Engine(synthetic.make_state_dict(), max_micro_batch=64)\n"
-        "px5 = synth.pixel_values(5, seed=71).to(torch.bfloat16).cuda()\n"
-        "px150 = synth.pixel_values(150, seed=72).to(torch.bfloat16).cuda()\n"
-        "out = {'h0': eng.hidden_states('vision', px5, 0).cpu(), 'e5': eng.encode_images(px5).cpu(),\n"
-        "       'e5b': eng.encode_images(px5).cpu(), 'e150': eng.encode_images(px150).cpu()}\n"
-        "torch.save(out, sys.argv[1])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    outp = tmp_path / "direct.pt"
-    r = subprocess.run([sys.executable, str(script), str(outp)], env=dict(os.environ, PLIP_PATCH_DIRECT="1"),
-                       capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stderr[-2000:]
-    got = torch.load(outp)
-    for k in ref:
-        assert torch.equal(got[k], ref[k]), (k, (got[k] - ref[k]).abs().max().item())
-
-
 def test_forward_on_host_inputs_equals_device_inputs(state_dict):
     """`model(**inputs)` with HOST tensors (the e2e path of bench.py): pixels are uploaded micro-batch by micro-batch on
     the engine's copy stream while the text tower / the previous micro-batch computes — same logits, bit for bit."""
