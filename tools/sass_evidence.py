@@ -39,7 +39,7 @@ def main():
     print("# SASS evidence (cuobjdump -sass plip_b200/libplip_b200.so, sm_100a), round 2: Blackwell-native instructions per kernel")
     print("# UTCHMMA = tcgen05.mma kind::f16, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA tensor load/store, UTCBAR = tcgen05.commit,")
     print("# UTCATOMSWS = tcgen05.alloc/dealloc, SYNCS = mbarrier ops, UCGABAR = cluster barrier, FFMA2/FMUL2/FADD2 = packed fp32 (fma.rn.f32x2 ...);")
-    print("# no HMMA (legacy mma.sync) anywhere.  gemm_kernel<CTA group, BLOCK_N, epilogue, fp16 operands>: epilogues 0 bias, 1 bias+GELU,")
+    print("# no HMMA (legacy mma.sync) anywhere.  gemm_kernel<CTA group, BLOCK_N, epilogue, fp16 operands, two-pair cluster (opt-in)>: epilogues 0 bias, 1 bias+GELU,")
     print("# 2 bias+residual, 3 patch, 4 f32, 5/6 LN-folded 0/1, 7 null, 8 similarity (row x column scales)")
     print()
     seen = set()
