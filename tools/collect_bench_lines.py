@@ -15,9 +15,15 @@ LABELS = {
     "r2d_bench_bf16_b": "packed-fp32 epilogues, bf16 operands (repeat)",
     "r2e_bench": "per-warp bias slices + graphs + tensor-core similarity (full extras)", "r2e_bench_mb512": "PLIP_BENCH_MB=512",
     "r2e_bench_nograph": "PLIP_GRAPH_MAX=0", "r2e_bench_cfg5_125k": "cfg5 with a 125k-tile gallery on one GPU (= one rank of N=8)",
+    "r2n_bench_a1": "two-pair-cluster A-B-A: default", "r2n_bench_quad": "two-pair-cluster A-B-A: PLIP_GEMM_QUAD=1",
+    "r2n_bench_a2": "two-pair-cluster A-B-A: default again", "r2o_bench": "with extra.last_layer_pruning_opt_in",
+    "r2q_bench": "software-pipelined 16-bit epilogue", "r2r_bench_a1": "pipelined fp32 epilogues (A)",
+    "r2r_bench_b": "PLIP_GEMM_F32_SERIAL=1 (B)", "r2r_bench_a2": "pipelined fp32 epilogues (A again)",
+    "r2s_bench": "END OF ROUND driver-style run of HEAD (slower box: 1447 MHz under the cap)",
+    "r2s_bench_bn256": "PLIP_GEMM_BN=256 forced on every GEMM (out_proj A/B)",
     "r2f_bench": "FINAL driver-style run", "r2f_bench_reference": "FINAL reference arm", "r2f_bench_cfg3": "FINAL cfg3 line",
 }
-KEEP_FULL = {"r2f_bench", "r2f_bench_reference", "r2f_bench_cfg3", "r2e_bench"}
+KEEP_FULL = {"r2f_bench", "r2f_bench_reference", "r2f_bench_cfg3", "r2e_bench", "r2s_bench"}
 
 
 def trim(b):
@@ -41,7 +47,13 @@ def main():
     res = {}
     for f in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "r2*.json")) + glob.glob(os.path.join(ROOT, "gpurun_out", "r2*.jsonl"))):
         key = os.path.basename(f).rsplit(".", 1)[0]
-        lines = [json.loads(l) for l in open(f) if l.strip().startswith("{")]
+        lines = []
+        for l in open(f):
+            if l.strip().startswith("{"):
+                try:
+                    lines.append(json.loads(l))
+                except json.JSONDecodeError:   # a pretty-printed (multi-line) JSON file, not a bench line
+                    break
         if not lines or "value" not in lines[0]:
             continue
         for i, b in enumerate(lines):
